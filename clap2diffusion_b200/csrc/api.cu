@@ -1,0 +1,94 @@
+// C-ABI dispatch for the dense contractions: picks the tcgen05 kernels (bf16) or the FFMA kernels (fp32
+// parity mode and shapes the tensor-core kernels do not take).  No CPU path exists.
+#include "common.cuh"
+
+namespace c2d {
+
+int linear_simt(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int,
+                int, int, int, cudaStream_t);
+int conv3x3_simt(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int,
+                 int, int, cudaStream_t);
+bool linear_tc_supported(const void*, const void*, int, int, int, int);
+int linear_tc(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int, int,
+              int, bool, cudaStream_t);
+bool conv3x3_tc_supported(const void*, const void*, int, int, int, int, int, int, int);
+int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int,
+               cudaStream_t);
+int attention_simt(const AttnParams&, int, int, cudaStream_t);
+bool attention_tc_supported(const AttnParams&, int B);
+int attention_tc(const AttnParams&, int B, cudaStream_t);
+
+}  // namespace c2d
+
+using namespace c2d;
+
+extern "C" {
+
+int c2d_linear(const void* x, const void* w, const float* bias, const float* rowvec, int rows_per_vec,
+               const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act, int dtype,
+               int impl, void* stream) {
+  C2D_REQUIRE(x && w && y, "linear: null pointer");
+  C2D_REQUIRE(M > 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, "linear: bad dims M=%d N=%d K=%d ldx=%d ldy=%d", M, N, K, ldx, ldy);
+  C2D_REQUIRE(!residual || ldr >= N, "linear: bad residual stride %d", ldr);
+  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_SILU, "linear: bad act %d", act);
+  C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "linear: bad dtype %d", dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool tc_ok = dtype == C2D_BF16 && linear_tc_supported(x, w, M, N, K, ldx);
+  if (impl == C2D_IMPL_TCGEN05) {
+    C2D_REQUIRE(tc_ok, "linear: tcgen05 path needs bf16, K %% 8 == 0, ldx %% 8 == 0, aligned pointers");
+    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
+  }
+  if (impl == C2D_IMPL_AUTO && tc_ok && M >= 64 && N >= 32)
+    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
+  return linear_simt(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, dtype, s);
+}
+
+int c2d_geglu_linear(const void* x, const void* w, const float* bias, void* y, int M, int F, int K, int packed, int dtype,
+                     int impl, void* stream) {
+  C2D_REQUIRE(x && w && y && M > 0 && F > 0 && K > 0, "geglu_linear: bad args");
+  C2D_REQUIRE(packed, "geglu_linear: only the packed (c2d_pack_geglu) weight layout is fused; use c2d_linear + c2d_geglu otherwise");
+  C2D_REQUIRE(dtype == C2D_BF16 && F % 64 == 0, "geglu_linear: fused path is bf16 with F %% 64 == 0");
+  C2D_REQUIRE(linear_tc_supported(x, w, M, 2 * F, K, K), "geglu_linear: K %% 8 / alignment");
+  (void)impl;
+  return linear_tc(x, w, bias, nullptr, 1, nullptr, y, M, 2 * F, K, K, F, 0, C2D_ACT_NONE, true, (cudaStream_t)stream);
+}
+
+int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y,
+                int B, int H, int W, int Cin, int Cout, int stride, int upsample2x, int dtype, int impl, void* stream) {
+  C2D_REQUIRE(x && w && y, "conv3x3: null pointer");
+  C2D_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: bad dims");
+  C2D_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride %d", stride);
+  C2D_REQUIRE(!(upsample2x && stride != 1), "conv3x3: upsample2x requires stride 1");
+  C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "conv3x3: bad dtype %d", dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  bool tc_ok = dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, upsample2x);
+  if (impl == C2D_IMPL_TCGEN05) {
+    C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, stride 1, no fused upsample, pow2 H/W, Cin %% 8 == 0, Cin >= 64");
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
+  }
+  if (impl == C2D_IMPL_AUTO && tc_ok && Cout >= 32)
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
+  return conv3x3_simt(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, upsample2x, dtype, s);
+}
+
+int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
+                  long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
+                  long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl, void* stream) {
+  C2D_REQUIRE(q && k && v && o, "attention: null pointer");
+  C2D_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nkv > 0 && d > 0, "attention: bad dims");
+  C2D_REQUIRE(d % 8 == 0, "attention: head_dim %d must be a multiple of 8", d);
+  C2D_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0,
+              "attention: strides must be multiples of 8 elements");
+  C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "attention: bad dtype %d", dtype);
+  AttnParams p = {q, k, v, o, Nq, Nkv, d, heads, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, mask};
+  cudaStream_t s = (cudaStream_t)stream;
+  bool tc_ok = dtype == C2D_BF16 && attention_tc_supported(p, B);
+  if (impl == C2D_IMPL_TCGEN05) {
+    C2D_REQUIRE(tc_ok, "attention: tcgen05 path does not take this shape (d=%d Nq=%d Nkv=%d)", d, Nq, Nkv);
+    return attention_tc(p, B, s);
+  }
+  if (impl == C2D_IMPL_AUTO && tc_ok) return attention_tc(p, B, s);
+  return attention_simt(p, B, dtype, s);
+}
+
+}  // extern "C"

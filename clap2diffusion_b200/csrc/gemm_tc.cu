@@ -1,0 +1,370 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: y = act(A . W^T + bias + rowvec) + residual, bf16 in, fp32 accumulate.
+//
+// One kernel, two A-operand producers:
+//   plain : A = x[M][K] (row stride ldx), 2-D TMA boxes {64 k, 128 rows}
+//   conv  : A = implicit im2col of an NHWC image for a 3x3 / pad-1 / stride-1 convolution.  The 128-pixel
+//           M-tile is a rectangle {bw x bh x bb} of the [B][H][W][C] tensor; for filter tap (ky,kx) the
+//           producer issues ONE 4-D TMA box at coordinates (c0, x0+kx-1, y0+ky-1, b0) -- the halo /
+//           zero padding comes from TMA's out-of-bounds zero fill, so im2col never exists in memory.
+// B = W[N][K] row-major (PyTorch Linear layout; conv weights packed [Cout][3][3][Cin]), 2-D TMA {64 k, BN rows}.
+// Both operands land in 128-byte-swizzled K-major smem tiles and feed tcgen05.mma (M=128, N=BN, K=16) with
+// the fp32 accumulator in TMEM.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..5 = epilogue (tcgen05.ld -> bias / time-embedding row vector / activation / GEGLU gate /
+// residual -> bf16 global stores).  3-stage mbarrier ring; 2 CTAs per SM so one CTA's epilogue overlaps
+// the other's main loop.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace c2d {
+
+using namespace tc;
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192;
+
+struct TcParams {
+  const float* bias;
+  const float* rowvec;
+  const bf16* residual;
+  bf16* y;
+  int M, N, K;
+  long long ldy, ldr;
+  int rows_per_vec;
+  int act;
+  int num_k_blocks;
+  // conv geometry
+  int HW, W, Cin, cblocks;
+};
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int get_encode() {
+  if (g_encode) return C2D_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return C2D_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return C2D_OK;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost-first; strides in BYTES for dims 1..rank-1.
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  int rc = get_encode();
+  if (rc) return rc;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims {%llu,%llu,%llu,%llu} stride0 %llu box {%u,%u,%u,%u} base %p",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, base);
+    return C2D_ERR_CUDA;
+  }
+  return C2D_OK;
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+};
+
+__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32], bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid >= 32) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 r;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
+      *reinterpret_cast<uint4*>(dst + g * 8) = r;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+template <int BN, bool CONV, bool GEGLU>
+__global__ void __launch_bounds__(TC_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tmem_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int b0 = 0, y0 = 0, x0 = 0;
+      if (CONV) {
+        b0 = m0 / p.HW;
+        int rem = m0 - b0 * p.HW;
+        y0 = rem / p.W;
+        x0 = rem - y0 * p.W;
+      }
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+        if (CONV) {
+          const int tap = kb / p.cblocks;
+          const int c0 = (kb - tap * p.cblocks) * TC_BK;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          tma_load_4d(sA, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b0);
+          tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
+        } else {
+          tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+          tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t a_desc = make_desc_k_sw128(a_addr);
+        const uint64_t b_desc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);          // smem slot reusable once these MMAs retire
+      }
+      umma_commit(tmem_full);            // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(m / p.rows_per_vec) * p.N : nullptr;
+    if (!GEGLU) {
+      const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+      const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int n = n0 + c * 32;
+        const int nvalid = p.N - n;
+        if (row_ok && nvalid > 0) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
+          }
+          if (rv) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(rv + n + j);
+          }
+          if (p.act != C2D_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.residual) {
+            const bf16* rp = p.residual + (long long)m * p.ldr + n;
+            if (vec_r && nvalid >= 32) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float f[8];
+                Vec8<bf16>::load(rp + g * 8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          store_bf16x32(p.y + (long long)m * p.ldy + n, v, vec_y, nvalid);
+        }
+      }
+    } else {
+      // GEGLU: tile columns [0,64) = a, [64,128) = gate for output columns n0/2 + [0,64)
+      const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+      const int F = p.N >> 1;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ra[32], rg[32];
+        tmem_ld_32x32(t_row + c * 32, ra);
+        tmem_ld_32x32(t_row + 64 + c * 32, rg);
+        tmem_ld_wait();
+        const int fo = (n0 >> 1) + c * 32;
+        const int nvalid = F - fo;
+        if (row_ok && nvalid > 0) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(ra[j]), g = __uint_as_float(rg[j]);
+            if (p.bias) { a += __ldg(p.bias + n0 + c * 32 + j); g += __ldg(p.bias + n0 + 64 + c * 32 + j); }
+            v[j] = a * gelu_erf(g);
+          }
+          store_bf16x32(p.y + (long long)m * p.ldy + fo, v, vec_y, nvalid);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool CONV, bool GEGLU>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return C2D_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM));
+  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool linear_tc_supported(const void* x, const void* w, int M, int N, int K, int ldx) {
+  return M >= 1 && N >= 8 && K >= 8 && K % 8 == 0 && ldx % 8 == 0 && al16(x) && al16(w);
+}
+
+int linear_tc(const void* x, const void* w, const float* bias, const float* rowvec, int rows_per_vec,
+              const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act, bool geglu,
+              cudaStream_t s) {
+  C2D_REQUIRE(linear_tc_supported(x, w, M, N, K, ldx),
+              "linear_tc: needs bf16, K %% 8 == 0, ldx %% 8 == 0, 16B-aligned x/w (M=%d N=%d K=%d ldx=%d)", M, N, K, ldx);
+  const int BN = geglu ? 128 : ((N % 160 == 0) ? 160 : 128);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t st[1] = {(uint64_t)ldx * 2};
+    uint32_t box[2] = {TC_BK, TC_BM};
+    int rc = make_tmap_bf16(&tmA, x, 2, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t st[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tmB, w, 2, dims, st, box);
+    if (rc) return rc;
+  }
+  TcParams p = {};
+  p.bias = bias; p.rowvec = rowvec; p.residual = reinterpret_cast<const bf16*>(residual); p.y = reinterpret_cast<bf16*>(y);
+  p.M = M; p.N = N; p.K = K; p.ldy = ldy; p.ldr = ldr;
+  p.rows_per_vec = rows_per_vec > 0 ? rows_per_vec : 1;
+  p.act = act;
+  p.num_k_blocks = ceil_div(K, TC_BK);
+  if (geglu) return launch_tc<128, false, true>(tmA, tmB, p, s);
+  if (BN == 160) return launch_tc<160, false, false>(tmA, tmB, p, s);
+  return launch_tc<128, false, false>(tmA, tmB, p, s);
+}
+
+static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int Cin, int Cout, int stride, int up) {
+  return stride == 1 && !up && Cin % 8 == 0 && Cin >= 64 && Cout >= 8 && is_pow2(W) && is_pow2(H) && al16(x) && al16(w) &&
+         ((long long)H * W >= 128 || 128 % (H * W) == 0);
+}
+
+int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
+               int H, int W, int Cin, int Cout, cudaStream_t s) {
+  C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, 1, 0),
+              "conv3x3_tc: needs stride 1, pow2 H/W, Cin %% 8 == 0, Cin >= 64 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+  const int bw = W < 128 ? W : 128;
+  const int bh = (128 / bw) < H ? (128 / bw) : H;
+  const int bb = 128 / (bw * bh);
+  const int BN = (Cout % 160 == 0) ? 160 : 128;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t st[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {TC_BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    int rc = make_tmap_bf16(&tmA, x, 4, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
+    uint64_t st[1] = {(uint64_t)9 * Cin * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tmB, w, 2, dims, st, box);
+    if (rc) return rc;
+  }
+  TcParams p = {};
+  p.bias = bias; p.rowvec = rowvec; p.residual = reinterpret_cast<const bf16*>(residual); p.y = reinterpret_cast<bf16*>(y);
+  p.M = B * H * W; p.N = Cout; p.K = 9 * Cin; p.ldy = Cout; p.ldr = Cout;
+  p.rows_per_vec = H * W;
+  p.act = C2D_ACT_NONE;
+  p.HW = H * W; p.W = W; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK);
+  p.num_k_blocks = 9 * p.cblocks;
+  if (BN == 160) return launch_tc<160, true, false>(tmA, tmB, p, s);
+  return launch_tc<128, true, false>(tmA, tmB, p, s);
+}
+
+int init_tc(int device) {
+  (void)device;
+  return get_encode();
+}
+
+}  // namespace c2d

@@ -1,0 +1,347 @@
+"""Thin torch-tensor front end over the C ABI (include/c2d.h).  PyTorch is used for device memory and
+streams only; every function marshals raw device pointers into libc2d on the current CUDA stream.
+
+Layout: activations are channels-last token tensors [B, N, C] (N = H*W); see c2d.h.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = _lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_TCGEN05
+ACT_NONE, ACT_GELU, ACT_SILU = _lib.ACT_NONE, _lib.ACT_GELU, _lib.ACT_SILU
+AUDIO_ADD, AUDIO_CONCAT = _lib.AUDIO_ADD, _lib.AUDIO_CONCAT
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"libc2d takes float32 or bfloat16 tensors, got {t.dtype}") from None
+
+
+def _dev(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise _lib.C2DError("libc2d has no CPU path: tensor is on " + str(t.device))
+    _lib.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+    return t
+
+
+def _rows(x: torch.Tensor):
+    """View [..., K] as (M, K, ld) without copying; requires unit inner stride and uniform row stride."""
+    if x.stride(-1) != 1:
+        raise ValueError("inner dimension must be contiguous")
+    K = x.shape[-1]
+    if x.dim() == 1:
+        return 1, K, K
+    M = 1
+    for s in x.shape[:-1]:
+        M *= s
+    ld = x.stride(-2)
+    # leading dims must be collapsible onto the row stride
+    exp = ld
+    for dim in range(x.dim() - 2, -1, -1):
+        if x.shape[dim] != 1 and x.stride(dim) != exp:
+            raise ValueError(f"tensor with shape {tuple(x.shape)} strides {x.stride()} is not a strided row matrix")
+        exp *= x.shape[dim]
+    return M, K, ld
+
+
+# ------------------------------------------------------------------------------------------------
+def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_per_vec=1, out=None,
+           impl=IMPL_AUTO):
+    """y = act(x @ w.T + bias + rowvec[row // rows_per_vec]) + residual.   w: [N, K] (nn.Linear layout)."""
+    _dev(x)
+    M, K, ldx = _rows(x)
+    N = w.shape[0]
+    assert w.shape[1] == K and w.is_contiguous() and w.dtype == x.dtype, (w.shape, K, w.dtype, x.dtype)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=x.dtype)
+    Mo, No, ldy = _rows(out)
+    assert Mo == M and No == N and out.dtype == x.dtype
+    ldr = 0
+    if residual is not None:
+        Mr, Nr, ldr = _rows(residual)
+        assert Mr == M and Nr == N and residual.dtype == x.dtype
+    check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                         int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
+                         impl, _stream()), "linear")
+    return out
+
+
+def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=IMPL_AUTO):
+    """Fused GEGLU projection; w_packed/bias_packed from pack_geglu()."""
+    _dev(x)
+    M, K, ldx = _rows(x)
+    assert ldx == K, "geglu_linear takes a dense x"
+    F = w_packed.shape[0] // 2
+    if out is None:
+        out = torch.empty(*x.shape[:-1], F, device=x.device, dtype=x.dtype)
+    check(lib.c2d_geglu_linear(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")), out.data_ptr(),
+                               M, F, K, 1, _dt(x), impl, _stream()), "geglu_linear")
+    return out
+
+
+def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, upsample=False, out=None,
+            impl=IMPL_AUTO):
+    """x [B,H,W,Cin] NHWC; w_packed [Cout,3,3,Cin]; returns [B,Ho,Wo,Cout]."""
+    _dev(x)
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert x.is_contiguous() and w_packed.is_contiguous() and tuple(w_packed.shape[1:]) == (3, 3, Cin)
+    Hin, Win = (2 * H, 2 * W) if upsample else (H, W)
+    Ho, Wo = (Hin - 1) // stride + 1, (Win - 1) // stride + 1
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=x.dtype)
+    assert out.is_contiguous() and out.numel() == B * Ho * Wo * Cout
+    if residual is not None:
+        assert residual.is_contiguous() and residual.numel() == out.numel() and residual.dtype == x.dtype
+    check(lib.c2d_conv3x3(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                          _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout, stride, int(bool(upsample)), _dt(x),
+                          impl, _stream()), "conv3x3")
+    return out
+
+
+_gn_ws = {}
+
+
+def _gn_workspace(device, n_doubles: int) -> torch.Tensor:
+    ws = _gn_ws.get(device)
+    if ws is None or ws.numel() < n_doubles:
+        ws = torch.empty(max(n_doubles, 8192), device=device, dtype=torch.float64)
+        _gn_ws[device] = ws
+    return ws
+
+
+def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_cat=None, out=None):
+    """x [B,N,C1] (+ optional x2 [B,N,C2] concatenated on channels) -> [B,N,C1+C2]."""
+    _dev(x)
+    B, C1 = x.shape[0], x.shape[-1]
+    N = x.numel() // (B * C1)
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x.dtype))
+    if out is None:
+        out = torch.empty(*x.shape[:-1], C1 + C2, device=x.device, dtype=x.dtype)
+    ws = _gn_workspace(x.device, B * groups * 2)
+    check(lib.c2d_group_norm(x.data_ptr(), _ptr(x2), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                             out.data_ptr(), _ptr(raw_cat), ws.data_ptr(), B, N, C1, C2, groups, float(eps),
+                             int(bool(silu)), _dt(x), _stream()), "group_norm")
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, *, out=None):
+    _dev(x)
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    M = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.c2d_layer_norm(x.data_ptr(), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                             out.data_ptr(), M, C, float(eps), _dt(x), _stream()), "layer_norm")
+    return out
+
+
+def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, out=None, impl=IMPL_AUTO):
+    """softmax(q k^T * scale) v per head.  q [B,Nq,heads*d], k/v [B,Nkv,heads*d]; strided views (e.g. slices
+    of a packed QKV buffer) are accepted as long as the inner dim is contiguous."""
+    _dev(q)
+    B, Nq, C = q.shape
+    Nkv = k.shape[1]
+    d = C // heads
+    assert k.shape[2] == C and v.shape[2] == C and v.shape[1] == Nkv
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    if out is None:
+        out = torch.empty(B, Nq, C, device=q.device, dtype=q.dtype)
+    assert out.stride(2) == 1
+    if scale is None:
+        scale = d ** -0.5
+    if mask is not None:
+        assert mask.dtype in (torch.bool, torch.uint8) and mask.is_contiguous() and tuple(mask.shape) == (B, Nkv)
+    check(lib.c2d_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nkv, d,
+                            q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0),
+                            v.stride(0), out.stride(0), float(scale), _ptr(mask), _dt(q), impl, _stream()),
+          "attention")
+    return out
+
+
+def audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode: int, *, out=None):
+    """AudioAttnProcessor context step (add / concat); see c2d.h."""
+    _dev(ehs)
+    B, T, D = ehs.shape
+    K, Da = audio.shape[1], audio.shape[2]
+    Hb = w1.shape[0]
+    assert ehs.is_contiguous() and audio.is_contiguous() and audio.dtype == ehs.dtype
+    assert w1.dtype == ehs.dtype and w2.dtype == ehs.dtype and w1.is_contiguous() and w2.is_contiguous()
+    Tout = T if mode == AUDIO_ADD else T + min(K, 4)
+    if out is None:
+        out = torch.empty(B, Tout, D, device=ehs.device, dtype=ehs.dtype)
+    check(lib.c2d_audio_context(ehs.data_ptr(), audio.data_ptr(), w1.data_ptr(), _f32(b1, "b1").data_ptr(),
+                                w2.data_ptr(), _f32(b2, "b2").data_ptr(), _ptr(_f32(alpha, "alpha")), out.data_ptr(),
+                                B, T, D, K, Da, Hb, mode, _dt(ehs), _stream()), "audio_context")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def timestep_embedding(t, dim: int = 320, *, out=None):
+    _dev(t)
+    t = _f32(t, "t")
+    B = t.numel()
+    if out is None:
+        out = torch.empty(B, dim, device=t.device, dtype=torch.float32)
+    check(lib.c2d_timestep_embedding(t.data_ptr(), out.data_ptr(), B, dim, _stream()), "timestep_embedding")
+    return out
+
+
+def unary(x, act=ACT_NONE, *, out_dtype=None, out=None):
+    """Elementwise activation and/or dtype cast."""
+    _dev(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    check(lib.c2d_unary(x.data_ptr(), out.data_ptr(), x.numel(), act, _dt(x), _dt(out), _stream()), "unary")
+    return out
+
+
+def cast(x, dtype, *, out=None):
+    return unary(x, ACT_NONE, out_dtype=dtype, out=out)
+
+
+def add(a, b, *, out=None):
+    _dev(a)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.dtype == b.dtype
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.c2d_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _dt(a), _stream()), "add")
+    return out
+
+
+def geglu(x, *, out=None):
+    _dev(x)
+    assert x.is_contiguous()
+    F = x.shape[-1] // 2
+    M = x.numel() // (2 * F)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], F, device=x.device, dtype=x.dtype)
+    check(lib.c2d_geglu(x.data_ptr(), out.data_ptr(), M, F, _dt(x), _stream()), "geglu")
+    return out
+
+
+def upsample2x(x, *, out=None):
+    _dev(x)
+    B, H, W, Cc = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, Cc, device=x.device, dtype=x.dtype)
+    check(lib.c2d_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _dt(x), _stream()), "upsample2x")
+    return out
+
+
+def concat(x1, x2, *, out=None):
+    _dev(x1)
+    assert x1.is_contiguous() and x2.is_contiguous() and x1.shape[:-1] == x2.shape[:-1] and x1.dtype == x2.dtype
+    C1, C2 = x1.shape[-1], x2.shape[-1]
+    rows = x1.numel() // C1
+    if out is None:
+        out = torch.empty(*x1.shape[:-1], C1 + C2, device=x1.device, dtype=x1.dtype)
+    check(lib.c2d_concat(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), rows, C1, C2, _dt(x1), _stream()), "concat")
+    return out
+
+
+def nchw_to_nhwc(x, dtype, *, out=None):
+    """fp32 [B,C,H,W] -> dtype [B,H,W,C]."""
+    _dev(x)
+    x = _f32(x, "x")
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty(B, H, W, Cc, device=x.device, dtype=dtype)
+    check(lib.c2d_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, Cc, H * W, _dt(out), _stream()), "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, *, out=None):
+    """dtype [B,H,W,C] -> fp32 [B,C,H,W]."""
+    _dev(x)
+    B, H, W, Cc = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, Cc, H, W, device=x.device, dtype=torch.float32)
+    check(lib.c2d_nhwc_to_nchw(x.data_ptr(), _f32(out, "out").data_ptr(), B, Cc, H * W, _dt(x), _stream()),
+          "nhwc_to_nchw")
+    return out
+
+
+def cfg_sched_step(eps2, x, xin2, guidance: float, coef, trace=None):
+    """In place: x <- ca*x + cb*(eps_u + g (eps_c - eps_u)); xin2 <- cat[x, x] * in_scale (NHWC, eps2.dtype).
+    coef: device fp32 tensor [3] = (ca, cb, in_scale)."""
+    _dev(eps2)
+    B = x.shape[0]
+    HW = x.shape[2] * x.shape[3]
+    assert eps2.is_contiguous() and xin2.is_contiguous() and eps2.shape[0] == 2 * B and xin2.dtype == eps2.dtype
+    assert coef.is_cuda and coef.numel() >= 3
+    check(lib.c2d_cfg_sched_step(eps2.data_ptr(), _f32(x, "x").data_ptr(), xin2.data_ptr(), _ptr(_f32(trace, "trace")),
+                                 B, HW, float(guidance), _f32(coef, "coef").data_ptr(), _dt(eps2), _stream()),
+          "cfg_sched_step")
+    return x
+
+
+def softmax_rows(x, scale: float = 1.0, *, out=None):
+    _dev(x)
+    assert x.is_contiguous()
+    N = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.c2d_softmax_rows(x.data_ptr(), out.data_ptr(), x.numel() // N, N, float(scale), _dt(x), _stream()),
+          "softmax_rows")
+    return out
+
+
+def transpose(x, *, out=None):
+    """[b, R, C] -> [b, C, R] (materialised)."""
+    _dev(x)
+    assert x.is_contiguous() and x.dim() == 3
+    b, R, Cc = x.shape
+    if out is None:
+        out = torch.empty(b, Cc, R, device=x.device, dtype=x.dtype)
+    check(lib.c2d_transpose(x.data_ptr(), out.data_ptr(), b, R, Cc, _dt(x), _stream()), "transpose")
+    return out
+
+
+def pack_conv3x3(w, dtype):
+    """[Cout,Cin,3,3] fp32 (diffusers) -> [Cout,3,3,Cin] dtype."""
+    _dev(w)
+    w = _f32(w, "w")
+    Cout, Cin = w.shape[0], w.shape[1]
+    out = torch.empty(Cout, 3, 3, Cin, device=w.device, dtype=dtype)
+    check(lib.c2d_pack_conv3x3(w.data_ptr(), out.data_ptr(), Cout, Cin, _dt(out), _stream()), "pack_conv3x3")
+    return out
+
+
+def pack_geglu(w, bias, dtype):
+    """diffusers ff.net.0.proj [2F,K] fp32 (+bias [2F]) -> row-interleaved (64-row a/g blocks) dtype weights."""
+    _dev(w)
+    w = _f32(w, "w")
+    F, K = w.shape[0] // 2, w.shape[1]
+    wo = torch.empty(2 * F, K, device=w.device, dtype=dtype)
+    bo = torch.empty(2 * F, device=w.device, dtype=torch.float32) if bias is not None else None
+    check(lib.c2d_pack_geglu(w.data_ptr(), _ptr(_f32(bias, "bias")), wo.data_ptr(), _ptr(bo), F, K, _dt(wo),
+                             _stream()), "pack_geglu")
+    return wo, bo

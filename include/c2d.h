@@ -1,0 +1,145 @@
+/* c2d.h -- C ABI of libc2d.so: the B200 (sm_100a) compute library behind the CLAP2Diffusion
+ * inference hot path.
+ *
+ * Boundary contract: plain `extern "C"` functions, raw DEVICE pointers + explicit
+ * sizes, a dtype enum, the caller's `cudaStream_t` (passed as void*), `int` status (0 = ok).  No torch
+ * types, no exceptions; the failure message is in c2d_last_error() (thread-local).  The caller
+ * (PyTorch) owns every buffer including workspaces; calls are asynchronous on the given stream and
+ * capturable into a CUDA graph.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point returns C2D_ERR_CUDA.
+ *
+ * Activation layout everywhere: channels-last tokens  x[b][n][c]  (n = y*W + x), i.e. NHWC.
+ * `dtype` is the storage type of activations AND matmul weights (C2D_F32: fp32 FFMA path used for
+ * the <=1e-4 parity mode; C2D_BF16: bf16 storage, fp32 accumulation, tcgen05 tensor cores).
+ * Biases, norm gains/shifts, statistics, latents and scheduler state are always fp32.
+ *
+ * Each entry point names the reference code it replaces (paths relative to /root/reference; the
+ * SD-1.5 UNet itself is third-party diffusers==0.23.1, requirements.txt:7, restated in oracle/sd15.py).
+ */
+#ifndef C2D_H_
+#define C2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2D_ABI_VERSION 1
+
+enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
+enum { C2D_F32 = 0, C2D_BF16 = 1 };
+enum { C2D_ACT_NONE = 0, C2D_ACT_GELU = 1, C2D_ACT_SILU = 2 };
+/* kernel family selector for the dense contractions */
+enum { C2D_IMPL_AUTO = 0, C2D_IMPL_SIMT = 1, C2D_IMPL_TCGEN05 = 2 };
+/* AudioAttnProcessor injection modes (models/audio_attention_processor.py:24) */
+enum { C2D_AUDIO_NONE = 0, C2D_AUDIO_ADD = 1, C2D_AUDIO_CONCAT = 2 };
+
+int c2d_abi_version(void);
+const char* c2d_last_error(void);
+/* Per-process, per-device one-time setup (driver entry points, max dynamic smem attributes). */
+int c2d_init(int device);
+/* Number of kernels this library has launched since load (claim for bench.py's gpu_launches). */
+unsigned long long c2d_launch_count(void);
+
+/* ---- dense layer:  y[M,N] = act(x[M,K] . w[N,K]^T + bias[N] + rowvec[m / rows_per_vec][N]) + residual[M,N]
+ * Replaces nn.Linear / 1x1 conv calls: attn.to_q/to_k/to_v/to_out[0]
+ * (models/audio_attention_processor.py:115,120-121,134), the projector / decomposer MLPs
+ * (models/audio_adapter_v4.py:43-48, models/hierarchical_audio_v4.py:110-116) and diffusers' FF / proj_in /
+ * proj_out / conv_shortcut / time MLP.  ldx/ldy/ldr are row strides in elements.  bias, rowvec,
+ * residual may be NULL.  rowvec is fp32 [ceil(M/rows_per_vec)][N] (the resnet time-embedding add). */
+int c2d_linear(const void* x, const void* w, const float* bias, const float* rowvec, int rows_per_vec,
+               const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act,
+               int dtype, int impl, void* stream);
+
+/* ---- GEGLU feed-forward input projection fused with the gate:
+ *  y[M,F] = (x.Wa^T + ba) * gelu(x.Wg^T + bg),  w = [Wa ; Wg] as stored by diffusers ff.net.0.proj ([2F,K]).
+ *  `w_packed` must be the row-interleaved form produced by c2d_pack_geglu (blocks of 64 rows: a,g,a,g..)
+ *  when impl resolves to TCGEN05; the SIMT path takes the original [2F,K] layout (packed = 0). */
+int c2d_geglu_linear(const void* x, const void* w, const float* bias, void* y, int M, int F, int K,
+                     int packed, int dtype, int impl, void* stream);
+
+/* ---- 3x3 convolution, padding 1, NHWC, weights [Cout][3][3][Cin] (tap-major, channel-minor).
+ *  y = conv(up2x?(x)) + bias + rowvec[b] + residual.   stride in {1,2}; upsample2x folds diffusers'
+ *  nearest x2 Upsample2D into the gather.  H,W are the INPUT dims (before upsample). */
+int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual,
+                void* y, int B, int H, int W, int Cin, int Cout, int stride, int upsample2x, int dtype,
+                int impl, void* stream);
+
+/* ---- GroupNorm (+ optional SiLU) over x[B][HW][C]; stats_ws: >= B*groups*2 doubles, zeroed by the call.
+ *  Optional second source: channels [C1, C1+C2) are read from x2[B][HW][C2] (the UNet skip concat
+ *  `cat([h, skip], dim=1)` is never materialised for the norm).  If raw_cat != NULL the concatenated,
+ *  un-normalised input is also written there (needed by the resnet shortcut). */
+int c2d_group_norm(const void* x, const void* x2, const float* gamma, const float* beta, void* y, void* raw_cat,
+                   double* stats_ws, int B, int HW, int C1, int C2, int groups, float eps, int silu, int dtype,
+                   void* stream);
+
+/* ---- LayerNorm over the last dim of x[M][C]. */
+int c2d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int M, int C, float eps,
+                   int dtype, void* stream);
+
+/* ---- multi-head attention core  o = softmax(q k^T * scale + mask) v.
+ *  q: [B][Nq][heads*d] with row stride ldq (elements) and batch stride bsq; same for k, v, o.
+ *  kv_len_valid: keys >= this index are masked out (used for padded K/V). mask: optional bool/uint8
+ *  [B][Nkv] (1 = keep).  Replaces head_to_batch_dim/get_attention_scores/bmm/batch_to_head_dim
+ *  (models/audio_attention_processor.py:124-131) and diffusers' SDPA self-attention. */
+int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
+                  long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
+                  long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl,
+                  void* stream);
+
+/* ---- AudioAttnProcessor context step (models/audio_attention_processor.py:85-109), step-invariant:
+ *  ehs_out = ehs + sigmoid(alpha) * mean_K(W2.gelu(W1.a + b1) + b2)            (ADD,   Tout = T)
+ *  ehs_out = [ehs ; adaptive_avg_pool_{<=4}(W2.gelu(W1.a + b1) + b2)]           (CONCAT, Tout = T+min(K,4))
+ *  ehs [B][T][D], audio [B][K][Da] (same dtype), w1 [Hb][Da], w2 [D][Hb], alpha: device fp32 scalar. */
+int c2d_audio_context(const void* ehs, const void* audio, const void* w1, const float* b1, const void* w2,
+                      const float* b2, const float* alpha, void* ehs_out, int B, int T, int D, int K, int Da,
+                      int Hb, int mode, int dtype, void* stream);
+
+/* ---- elementwise / layout ------------------------------------------------------------------- */
+/* sinusoidal timestep embedding, flip_sin_to_cos, out fp32 [B][dim]: cat[cos, sin] */
+int c2d_timestep_embedding(const float* t, float* out, int B, int dim, void* stream);
+/* y = act(x) elementwise over n elements; x dtype_in -> y dtype_out (casts included) */
+int c2d_unary(const void* x, void* y, long long n, int act, int dtype_in, int dtype_out, void* stream);
+/* y = a + b (same dtype) */
+int c2d_add(const void* a, const void* b, void* y, long long n, int dtype, void* stream);
+/* y[M,F] = x[M,0:F] * gelu(x[M,F:2F]) */
+int c2d_geglu(const void* x, void* y, int M, int F, int dtype, void* stream);
+/* nearest 2x upsample of x[B][H][W][C] -> y[B][2H][2W][C] */
+int c2d_upsample2x(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+/* y[B][HW][C1+C2] = cat(x1, x2) on channels */
+int c2d_concat(const void* x1, const void* x2, void* y, long long rows, int C1, int C2, int dtype, void* stream);
+/* fp32 NCHW [B][C][HW] -> dtype NHWC [B][HW][C]  and back */
+int c2d_nchw_to_nhwc(const float* x, void* y, int B, int C, int HW, int dtype, void* stream);
+int c2d_nhwc_to_nchw(const void* x, float* y, int B, int C, int HW, int dtype, void* stream);
+
+/* ---- fused classifier-free guidance + scheduler update:
+ *  eps2: dtype NHWC [2B][HW][4] = cat[uncond, cond];  eps = eu + g (ec - eu);
+ *  x (fp32 NCHW [B][4][HW]) <- ca * x + cb * eps      (DDIM eta=0:  ca, cb from (t, t_prev);
+ *                                                       Euler:       ca = 1, cb = sigma_next - sigma)
+ *  then writes the next UNet input xin2 (dtype NHWC [2B][HW][4]) = cat[x, x] * in_scale
+ *  (in_scale = 1 for DDIM, 1/sqrt(sigma_next^2+1) for Euler).  coef = DEVICE fp32 {ca, cb, in_scale} so one
+ *  captured CUDA graph serves every step.  Optionally records x to trace (fp32). */
+int c2d_cfg_sched_step(const void* eps2, float* x, void* xin2, float* trace, int B, int HW, float guidance,
+                       const float* coef, int dtype, void* stream);
+
+/* row softmax y = softmax(x * scale) over the last dim of x[M][N]; batched transpose y[b][C][R] = x[b][R][C].
+ * Used by the materialised attention route for head dims the flash kernels do not take
+ * (AutoencoderKL mid-block attention, d = 512; AudioTokenGenerator single-head d = 768,
+ * models/audio_adapter_v4.py:101-108). */
+int c2d_softmax_rows(const void* x, void* y, int M, int N, float scale, int dtype, void* stream);
+int c2d_transpose(const void* x, void* y, int batch, int R, int C, int dtype, void* stream);
+
+/* ---- weight packing helpers (run once at load time) ------------------------------------------ */
+/* [Cout][Cin][3][3] fp32 (PyTorch/diffusers layout) -> [Cout][3][3][Cin] dtype */
+int c2d_pack_conv3x3(const float* w, void* out, int Cout, int Cin, int dtype, void* stream);
+/* diffusers GEGLU proj [2F][K] fp32 -> row-interleaved (64-row blocks a,g,a,g,...) dtype [2F][K];
+ * bias [2F] -> interleaved the same way (fp32). */
+int c2d_pack_geglu(const float* w, const float* bias, void* w_out, float* bias_out, int F, int K, int dtype,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2D_H_ */
