@@ -57,6 +57,11 @@ SIGNATURES = {
     "c2d_cfg_sched_step": [_p, _p, _p, _p, _i, _i, _f, _p, _i, _p],
     "c2d_softmax_rows": [_p, _p, _i, _i, _f, _i, _p],
     "c2d_transpose": [_p, _p, _i, _i, _i, _i, _p],
+    "c2d_bcast_add": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "c2d_hier_assign": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_hier_route": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "c2d_norm_scale": [_p, _p, _i, _i, _i, _f, _i, _i, _p],
+    "c2d_legacy_combine": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }

@@ -15,6 +15,7 @@ bool conv3x3_tc_supported(const void*, const void*, int, int, int, int, int, int
 int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int,
                cudaStream_t);
 int attention_simt(const AttnParams&, int, int, cudaStream_t);
+int attention_small(const AttnParams&, int, int, cudaStream_t);
 bool attention_tc_supported(const AttnParams&, int B);
 int attention_tc(const AttnParams&, int B, cudaStream_t);
 
@@ -76,12 +77,16 @@ int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, i
                   long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl, void* stream) {
   C2D_REQUIRE(q && k && v && o, "attention: null pointer");
   C2D_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nkv > 0 && d > 0, "attention: bad dims");
-  C2D_REQUIRE(d % 8 == 0, "attention: head_dim %d must be a multiple of 8", d);
-  C2D_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0,
-              "attention: strides must be multiples of 8 elements");
   C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "attention: bad dtype %d", dtype);
   AttnParams p = {q, k, v, o, Nq, Nkv, d, heads, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, mask};
   cudaStream_t s = (cudaStream_t)stream;
+  // tiny problems / head dims beyond the flash kernels (AudioTokenGenerator single head d=768): warp-per-query kernel
+  const bool vec_ok = d % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 &&
+                      bsv % 8 == 0 && (reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                                       reinterpret_cast<uintptr_t>(v)) % 32 == 0;
+  if (impl != C2D_IMPL_TCGEN05 && Nkv <= 128 && (d > 160 || !vec_ok)) return attention_small(p, B, dtype, s);
+  C2D_REQUIRE(vec_ok, "attention: head_dim and strides must be multiples of 8 elements and pointers 32B-aligned "
+                      "(or Nkv <= 128 for the small-attention kernel)");
   bool tc_ok = dtype == C2D_BF16 && attention_tc_supported(p, B);
   if (impl == C2D_IMPL_TCGEN05) {
     C2D_REQUIRE(tc_ok, "attention: tcgen05 path does not take this shape (d=%d Nq=%d Nkv=%d)", d, Nq, Nkv);

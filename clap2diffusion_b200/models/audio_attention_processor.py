@@ -1,0 +1,215 @@
+"""Drop-in for the reference's ``models/audio_attention_processor.py`` (AudioAttnProcessor :13-145,
+AudioProcessorManager :148-267) with the compute behind libc2d's C ABI.
+
+Same class names, constructor arguments, ``state_dict()`` keys (``alpha``, ``audio_proj.0.*``,
+``audio_proj.3.*``) and the diffusers processor call convention
+``proc(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+**cross_attention_kwargs)`` with audio arriving as ``cross_attention_kwargs['audio'][level]``.
+
+What differs from the reference (by design, results identical):
+  * the audio injection + K/V projections are step-invariant, so they are exposed separately
+    (``prepare`` -> cached K/V, ``attend`` -> per-step work); ``__call__`` = prepare + attend;
+  * attention probabilities are never materialised (flash kernel), no head permutes;
+  * CUDA only -- a CPU tensor raises ``C2DError`` (no fallback).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._lib import C2DError
+
+_MODES = {"add": ops.AUDIO_ADD, "concat": ops.AUDIO_CONCAT}
+
+
+class _CastCache:
+    """Device copies of parameters in the compute dtype, refreshed when the parameter changes."""
+
+    def __init__(self):
+        self._c: Dict[Any, Any] = {}
+
+    def get(self, t: torch.Tensor, dtype: torch.dtype, key=None) -> torch.Tensor:
+        t = t.detach()
+        if t.dtype == dtype and t.is_contiguous():
+            return t
+        k = (key if key is not None else id(t), dtype)
+        hit = self._c.get(k)
+        if hit is not None and hit[0] == (t._version, t.data_ptr()):
+            return hit[1]
+        out = ops.cast(t.contiguous(), dtype) if t.dtype in (torch.float32, torch.bfloat16) else t.to(dtype)
+        self._c[k] = ((t._version, t.data_ptr()), out)
+        return out
+
+
+def _weight(mod) -> torch.Tensor:
+    return mod.weight
+
+
+def _to_out_linear(attn):
+    to_out = attn.to_out
+    return to_out[0] if isinstance(to_out, (list, tuple, nn.ModuleList, nn.Sequential)) else to_out
+
+
+class AudioAttnProcessor(nn.Module):
+    """Audio-conditioned cross-attention processor (Add-FiLM or KV-concat)."""
+
+    def __init__(self, level: str, audio_dim: int = 768, hidden_dim: int = 768, mode: str = "add",
+                 dropout: float = 0.1, bottleneck_dim: int = 64):
+        super().__init__()
+        self.level = level
+        self.mode = mode
+        # parameter containers only (indices 0 and 3 keep the reference's state-dict keys)
+        self.audio_proj = nn.Sequential(nn.Linear(audio_dim, bottleneck_dim), nn.GELU(), nn.Dropout(dropout),
+                                        nn.Linear(bottleneck_dim, hidden_dim))
+        self.alpha = nn.Parameter(torch.zeros(1))
+        self._cache = _CastCache()
+
+    # ---- step-invariant part -------------------------------------------------------------------
+    def context(self, encoder_hidden_states: torch.Tensor, audio_tokens: Optional[torch.Tensor]) -> torch.Tensor:
+        """Text states with the audio injected (reference :85-109).  Falls through unchanged when there
+        is no audio for this level or the mode is unknown (reference :80,:86,:91,:99)."""
+        if audio_tokens is None or self.mode not in _MODES:
+            return encoder_hidden_states
+        dt = encoder_hidden_states.dtype
+        a = audio_tokens if audio_tokens.dtype == dt else ops.cast(audio_tokens.contiguous(), dt)
+        l0, l3 = self.audio_proj[0], self.audio_proj[3]
+        c = self._cache
+        return ops.audio_context(encoder_hidden_states.contiguous(), a.contiguous(),
+                                 c.get(l0.weight, dt, "w1"), c.get(l0.bias, torch.float32, "b1"),
+                                 c.get(l3.weight, dt, "w2"), c.get(l3.bias, torch.float32, "b2"),
+                                 c.get(self.alpha, torch.float32, "alpha"), _MODES[self.mode])
+
+    def _kv_weight(self, attn, dt) -> torch.Tensor:
+        wk, wv = _weight(attn.to_k).detach(), _weight(attn.to_v).detach()
+        key = ("wkv", id(attn), dt)
+        hit = self._cache._c.get(key)
+        ver = (wk._version, wv._version, wk.data_ptr(), wv.data_ptr())
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w = torch.cat([self._cache.get(wk, dt, ("wk", id(attn))), self._cache.get(wv, dt, ("wv", id(attn)))], dim=0)
+        self._cache._c[key] = (ver, w.contiguous())
+        return self._cache._c[key][1]
+
+    def prepare(self, attn, encoder_hidden_states: torch.Tensor, audio: Optional[Dict[str, torch.Tensor]] = None):
+        """K/V for this site: [B, T', 2C] = context(ehs, audio[level]) @ [Wk; Wv]^T (reference :120-121)."""
+        tokens = audio.get(self.level) if isinstance(audio, dict) else None
+        ehs = self.context(encoder_hidden_states, tokens)
+        return ops.linear(ehs, self._kv_weight(attn, ehs.dtype))
+
+    # ---- per-step part -------------------------------------------------------------------------
+    def attend(self, attn, hidden_states: torch.Tensor, kv: torch.Tensor, residual: Optional[torch.Tensor] = None,
+               scale: float = 1.0) -> torch.Tensor:
+        """to_q -> softmax(q k^T d^-1/2) v -> to_out[0] (+ residual).  hidden_states [B,N,C]."""
+        dt = hidden_states.dtype
+        c = self._cache
+        C = kv.shape[-1] // 2
+        q = ops.linear(hidden_states, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
+        d = C // attn.heads
+        o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=float(getattr(attn, "scale", d ** -0.5)) * scale)
+        out_lin = _to_out_linear(attn)
+        bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
+        return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual)
+
+    # ---- diffusers processor protocol ----------------------------------------------------------
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
+                 scale: float = 1.0, **cross_attention_kwargs) -> torch.Tensor:
+        if not hidden_states.is_cuda and not ops.TEST_DOUBLE:
+            raise C2DError("AudioAttnProcessor runs on CUDA only (libc2d has no CPU path)")
+        if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "norm_cross", None):
+            raise C2DError("spatial_norm / norm_cross attention variants are not on the SD-1.5 path")
+        if attention_mask is not None:
+            raise C2DError("attention_mask is not supported (always None on the SD-1.5 path)")
+        x = hidden_states
+        nd = x.dim()
+        if nd == 4:                                   # [B,C,H,W] -> [B,HW,C]   (reference :67-70)
+            B, Cc, H, W = x.shape
+            x = ops.transpose(x.reshape(B, Cc, H * W).contiguous())
+        x = x.contiguous()
+        if encoder_hidden_states is None:
+            # reference quirk (:117-121): K/V are projected from the Q-projected states
+            dt = x.dtype
+            c = self._cache
+            q = ops.linear(x, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
+            if scale != 1.0:
+                raise C2DError("scale != 1 with encoder_hidden_states=None is not supported")
+            k = ops.linear(q, c.get(_weight(attn.to_k), dt, ("wk", id(attn))))
+            v = ops.linear(q, c.get(_weight(attn.to_v), dt, ("wv", id(attn))))
+            o = ops.attention(q, k, v, attn.heads, scale=float(getattr(attn, "scale", (q.shape[-1] // attn.heads) ** -0.5)))
+            out_lin = _to_out_linear(attn)
+            bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
+            out = ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias)
+        else:
+            ehs = encoder_hidden_states
+            if ehs.dtype != x.dtype:
+                ehs = ops.cast(ehs.contiguous(), x.dtype)
+            kv = self.prepare(attn, ehs, cross_attention_kwargs.get("audio"))
+            res = x if getattr(attn, "residual_connection", False) and nd != 4 else None
+            out = self.attend(attn, x, kv, residual=res, scale=scale)
+        if nd == 4:                                   # back to [B,C,H,W] (reference :137-138)
+            out = ops.transpose(out).reshape(B, Cc, H, W)
+            if getattr(attn, "residual_connection", False):
+                out = ops.add(out, hidden_states.contiguous())
+        if float(getattr(attn, "rescale_output_factor", 1.0)) != 1.0:
+            raise C2DError("rescale_output_factor != 1 is not on the SD-1.5 path")
+        return out
+
+    forward = __call__
+
+
+class AudioProcessorManager:
+    """Maps one shared AudioAttnProcessor per level onto the UNet's attn2 sites (reference :148-267)."""
+
+    LEVEL_RULES = (("mid_block", "mid"), ("down_blocks.0", "early"), ("down_blocks.1", "early"),
+                   ("down_blocks.2", "late"), ("down_blocks.3", "late"), ("up_blocks.0", "late"),
+                   ("up_blocks.1", "late"), ("up_blocks.2", "mid"), ("up_blocks.3", "mid"))
+
+    def __init__(self, unet):
+        self.unet = unet
+        self.processors: Dict[str, Any] = {}
+        self.level_mapping = self._create_level_mapping()
+
+    def _create_level_mapping(self) -> Dict[str, list]:
+        mapping: Dict[str, list] = {"early": [], "mid": [], "late": []}
+        for name in self.unet.attn_processors.keys():
+            if "attn1" in name:                       # self-attention keeps its processor
+                continue
+            level = "mid"
+            for key, lvl in self.LEVEL_RULES:
+                if key in name:
+                    level = lvl
+                    break
+            mapping[level].append(name)
+        return mapping
+
+    def setup_processors(self, audio_dim: int = 768, hidden_dim: Optional[int] = None, mode: str = "add",
+                         dropout: float = 0.1):
+        if hidden_dim is None:
+            hidden_dim = 768
+            for name in self.unet.attn_processors:
+                if "attn2" not in name:
+                    continue
+                try:
+                    mod = self.unet.get_submodule(name.rsplit(".", 1)[0])
+                except (AttributeError, KeyError):
+                    continue
+                if hasattr(mod, "to_k"):
+                    w = mod.to_k.weight
+                    hidden_dim = getattr(mod.to_k, "in_features", w.shape[1])
+                    break
+        new_processors = dict(self.unet.attn_processors)
+        for level, names in self.level_mapping.items():
+            proc = AudioAttnProcessor(level=level, audio_dim=audio_dim, hidden_dim=hidden_dim, mode=mode, dropout=dropout)
+            for name in names:
+                new_processors[name] = proc
+        self.unet.set_attn_processor(new_processors)
+        self.processors = new_processors
+        print("Setup audio processors:")
+        for lvl in ("early", "mid", "late"):
+            print(f"  {lvl.capitalize()} blocks: {len(self.level_mapping[lvl])}")
+
+    def get_audio_kwargs(self, routed_tokens: Dict[str, torch.Tensor]) -> Dict:
+        return {"audio": routed_tokens}

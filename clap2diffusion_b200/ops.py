@@ -16,6 +16,10 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = _lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_T
 ACT_NONE, ACT_GELU, ACT_SILU = _lib.ACT_NONE, _lib.ACT_GELU, _lib.ACT_SILU
 AUDIO_ADD, AUDIO_CONCAT = _lib.AUDIO_ADD, _lib.AUDIO_CONCAT
 
+# Set ONLY by tests/torch_ops.py while it swaps these functions for torch doubles (host-logic tests on a
+# machine without a GPU).  The product never sets it; with it False every op demands CUDA tensors.
+TEST_DOUBLE = False
+
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
 
@@ -345,3 +349,67 @@ def pack_geglu(w, bias, dtype):
     check(lib.c2d_pack_geglu(w.data_ptr(), _ptr(_f32(bias, "bias")), wo.data_ptr(), _ptr(bo), F, K, _dt(wo),
                              _stream()), "pack_geglu")
     return wo, bo
+
+
+# ------------------------------------------------------------------------------------------------
+# audio-conditioning side
+# ------------------------------------------------------------------------------------------------
+def bcast_add(a, b, B: int, K: int, D: int, a_mode: int, b_mode: int, *, out=None):
+    """out[B,K,D] = a + b; mode 0 = [B,K,D], 1 = [B,1,D] (broadcast over tokens), 2 = [1,K,D] (over batch)."""
+    _dev(a)
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
+    if out is None:
+        out = torch.empty(B, K, D, device=a.device, dtype=a.dtype)
+    check(lib.c2d_bcast_add(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, K, D, a_mode, b_mode, _dt(a), _stream()),
+          "bcast_add")
+    return out
+
+
+def hier_assign(tokens, anchors, w1, b1, w2, b2, temperature):
+    """Soft level assignments fp32 [B,K,L]; tokens [B,K,D]; temperature: device fp32 scalar tensor."""
+    _dev(tokens)
+    B, K, D = tokens.shape
+    L, Hg = anchors.shape[0], w1.shape[0]
+    assert tokens.is_contiguous() and anchors.is_contiguous() and w1.is_contiguous() and w2.is_contiguous()
+    out = torch.empty(B, K, L, device=tokens.device, dtype=torch.float32)
+    check(lib.c2d_hier_assign(tokens.data_ptr(), anchors.data_ptr(), w1.data_ptr(), _f32(b1, "b1").data_ptr(),
+                              w2.data_ptr(), _f32(b2, "b2").data_ptr(), _f32(temperature, "temperature").data_ptr(),
+                              out.data_ptr(), B * K, D, L, Hg, _dt(tokens), _stream()), "hier_assign")
+    return out
+
+
+def hier_route(tok10, assign, hw, routing, gates):
+    """Returns (early, mid, late) routed tokens, each [B,K,D] in tok10.dtype."""
+    _dev(tok10)
+    B, K, D = tok10.shape
+    assert tok10.is_contiguous() and assign.shape[-1] == 3
+    outs = [torch.empty_like(tok10) for _ in range(3)]
+    check(lib.c2d_hier_route(tok10.data_ptr(), _f32(assign, "assign").data_ptr(), _ptr(_f32(hw, "hw")),
+                             _f32(routing, "routing").data_ptr(), _f32(gates, "gates").data_ptr(),
+                             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), B, K, D, _dt(tok10),
+                             _stream()), "hier_route")
+    return tuple(outs)
+
+
+def norm_scale(x, target: float = 60.0, per_sample: bool = False, *, out=None):
+    _dev(x)
+    B, K, D = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.c2d_norm_scale(x.data_ptr(), out.data_ptr(), B, K, D, float(target), int(bool(per_sample)), _dt(x),
+                             _stream()), "norm_scale")
+    return out
+
+
+def legacy_combine(fg, bg, amb, hierarchy_weights, D: int):
+    """cat(fg*w0, bg*w1, amb*w2) with w = softmax(hierarchy_weights); fg [B,nf*D] etc. -> [B,nf+nb+na,D]."""
+    _dev(fg)
+    B = fg.shape[0]
+    nf, nb, na = fg.shape[1] // D, bg.shape[1] // D, amb.shape[1] // D
+    assert fg.is_contiguous() and bg.is_contiguous() and amb.is_contiguous()
+    out = torch.empty(B, nf + nb + na, D, device=fg.device, dtype=fg.dtype)
+    check(lib.c2d_legacy_combine(fg.data_ptr(), bg.data_ptr(), amb.data_ptr(),
+                                 _f32(hierarchy_weights, "hierarchy_weights").data_ptr(), out.data_ptr(), B, nf, nb,
+                                 na, D, _dt(fg), _stream()), "legacy_combine")
+    return out

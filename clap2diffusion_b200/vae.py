@@ -1,0 +1,166 @@
+"""AutoencoderKL decoder of SD-1.5 (SURVEY.md App. A, row 15 of §8a) on libc2d kernels.
+
+Needed for the decoded-image PSNR criterion and for true images/s.  Same engine conventions as
+``unet.py``: channels-last activations, packed 3x3 weights, GroupNorm+SiLU fused, shortcut folded into
+conv2's residual.  The single-head mid-block attention (4096 tokens, d = 512) goes through the
+tensor-core GEMM twice (QK^T, PV) with a row-softmax kernel in between.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import ops
+
+VAE_BLOCK_OUT = (128, 256, 512, 512)
+VAE_SCALING = 0.18215
+GROUPS = 32
+EPS = 1e-6
+
+
+class VAEDecoder:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dtype=torch.bfloat16,
+                 impl: int = ops.IMPL_AUTO):
+        self.device, self.dtype, self.impl = torch.device(device), dtype, impl
+        self._sd = state_dict
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack()
+        self._sd = None
+
+    # ------------------------------------------------------------------ weights
+    def _dev32(self, name):
+        return self._sd[name].detach().to(self.device, torch.float32).contiguous()
+
+    def _cast(self, w):
+        return w if self.dtype == torch.float32 else ops.cast(w.contiguous(), self.dtype)
+
+    def _conv(self, p):
+        self.w[f"{p}.weight"] = ops.pack_conv3x3(self._dev32(f"{p}.weight"), self.dtype)
+        self.w[f"{p}.bias"] = self._dev32(f"{p}.bias")
+
+    def _lin(self, p):
+        w = self._dev32(f"{p}.weight")
+        self.w[f"{p}.weight"] = self._cast(w.reshape(w.shape[0], -1))
+        self.w[f"{p}.bias"] = self._dev32(f"{p}.bias")
+
+    def _norm(self, p):
+        self.w[f"{p}.weight"], self.w[f"{p}.bias"] = self._dev32(f"{p}.weight"), self._dev32(f"{p}.bias")
+
+    def _resnet(self, p, cin, cout):
+        self._norm(f"{p}.norm1"); self._conv(f"{p}.conv1"); self._norm(f"{p}.norm2"); self._conv(f"{p}.conv2")
+        if cin != cout:
+            self._lin(f"{p}.conv_shortcut")
+
+    def _pack(self):
+        # post_quant_conv (1x1, 4->4) with the 1/0.18215 latent scaling folded into its weight
+        w = self._dev32("post_quant_conv.weight").reshape(4, 4) / VAE_SCALING
+        self.w["post_quant_conv.weight"] = self._cast(w)
+        self.w["post_quant_conv.bias"] = self._dev32("post_quant_conv.bias")
+        c = VAE_BLOCK_OUT[-1]
+        self._conv("decoder.conv_in")
+        self._resnet("decoder.mid_block.resnets.0", c, c)
+        a = "decoder.mid_block.attentions.0"
+        self._norm(f"{a}.group_norm")
+        wq, wk, wv = (self._dev32(f"{a}.{n}.weight") for n in ("to_q", "to_k", "to_v"))
+        self.w[f"{a}.qkv.weight"] = self._cast(torch.cat([wq, wk, wv], 0))
+        self.w[f"{a}.qkv.bias"] = torch.cat([self._dev32(f"{a}.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0).contiguous()
+        self._lin(f"{a}.to_out.0")
+        self._resnet("decoder.mid_block.resnets.1", c, c)
+        prev = c
+        for i, cout in enumerate(reversed(VAE_BLOCK_OUT)):
+            for j in range(3):
+                self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+            if i < 3:
+                self._conv(f"decoder.up_blocks.{i}.upsamplers.0.conv")
+            prev = cout
+        self._norm("decoder.conv_norm_out")
+        self._conv("decoder.conv_out")
+
+    # ------------------------------------------------------------------ forward
+    def _res(self, p, x):
+        w = self.w
+        h = ops.group_norm(x, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], GROUPS, EPS, True)
+        h = ops.conv3x3(h, w[f"{p}.conv1.weight"], w[f"{p}.conv1.bias"], impl=self.impl)
+        h = ops.group_norm(h, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], GROUPS, EPS, True)
+        sc = x
+        if f"{p}.conv_shortcut.weight" in w:
+            sc = ops.linear(x, w[f"{p}.conv_shortcut.weight"], w[f"{p}.conv_shortcut.bias"], impl=self.impl)
+        return ops.conv3x3(h, w[f"{p}.conv2.weight"], w[f"{p}.conv2.bias"], residual=sc, impl=self.impl)
+
+    def _mid_attention(self, x):
+        w = self.w
+        a = "decoder.mid_block.attentions.0"
+        B, H, W, C = x.shape
+        N = H * W
+        xf = x.view(B, N, C)
+        hn = ops.group_norm(xf, w[f"{a}.group_norm.weight"], w[f"{a}.group_norm.bias"], GROUPS, EPS, False)
+        qkv = ops.linear(hn, w[f"{a}.qkv.weight"], w[f"{a}.qkv.bias"], impl=self.impl)          # [B,N,3C]
+        o = torch.empty(B, N, C, device=x.device, dtype=x.dtype)
+        for b in range(B):           # single head, d = C = 512: materialised scores per image
+            q, k, v = qkv[b, :, :C], qkv[b, :, C:2 * C], qkv[b, :, 2 * C:]
+            s = ops.linear(q, k.contiguous(), impl=self.impl)                                    # q k^T  [N,N]
+            p = ops.softmax_rows(s, scale=C ** -0.5)
+            vt = ops.transpose(v.contiguous().view(1, N, C)).view(C, N)                          # [C,N]
+            ops.linear(p, vt, out=o[b], impl=self.impl)                                          # p v    [N,C]
+        out = ops.linear(o, w[f"{a}.to_out.0.weight"], w[f"{a}.to_out.0.bias"], residual=xf, impl=self.impl)
+        return out.view(B, H, W, C)
+
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """z fp32 NCHW [B,4,h,w] (scaled latents) -> image fp32 NCHW [B,3,8h,8w]."""
+        w = self.w
+        x = ops.nchw_to_nhwc(z.contiguous().float(), self.dtype)
+        h = ops.linear(x, w["post_quant_conv.weight"], w["post_quant_conv.bias"], impl=self.impl)
+        h = ops.conv3x3(h, w["decoder.conv_in.weight"], w["decoder.conv_in.bias"], impl=self.impl)
+        h = self._res("decoder.mid_block.resnets.0", h)
+        h = self._mid_attention(h)
+        h = self._res("decoder.mid_block.resnets.1", h)
+        for i in range(4):
+            for j in range(3):
+                h = self._res(f"decoder.up_blocks.{i}.resnets.{j}", h)
+            if i < 3:
+                n = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                if self.dtype == torch.bfloat16:
+                    h = ops.conv3x3(ops.upsample2x(h), w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl)
+                else:
+                    h = ops.conv3x3(h, w[f"{n}.weight"], w[f"{n}.bias"], upsample=True, impl=self.impl)
+        h = ops.group_norm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], GROUPS, EPS, True)
+        h = ops.conv3x3(h, w["decoder.conv_out.weight"], w["decoder.conv_out.bias"], impl=self.impl)
+        return ops.nhwc_to_nchw(h)
+
+
+def param_shapes() -> Dict[str, tuple]:
+    """diffusers state-dict names -> shapes of the AutoencoderKL decoder + post_quant_conv (49,490,199)."""
+    out: Dict[str, tuple] = {}
+
+    def conv(n, cin, cout, k):
+        out[f"{n}.weight"] = (cout, cin, k, k)
+        out[f"{n}.bias"] = (cout,)
+
+    def norm(n, c):
+        out[f"{n}.weight"] = (c,)
+        out[f"{n}.bias"] = (c,)
+
+    def resnet(n, cin, cout):
+        norm(f"{n}.norm1", cin); conv(f"{n}.conv1", cin, cout, 3); norm(f"{n}.norm2", cout); conv(f"{n}.conv2", cout, cout, 3)
+        if cin != cout:
+            conv(f"{n}.conv_shortcut", cin, cout, 1)
+
+    c = VAE_BLOCK_OUT[-1]
+    conv("post_quant_conv", 4, 4, 1); conv("decoder.conv_in", 4, c, 3)
+    resnet("decoder.mid_block.resnets.0", c, c)
+    a = "decoder.mid_block.attentions.0"
+    norm(f"{a}.group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out[f"{a}.{n}.weight"] = (c, c)
+        out[f"{a}.{n}.bias"] = (c,)
+    resnet("decoder.mid_block.resnets.1", c, c)
+    prev = c
+    for i, cout in enumerate(reversed(VAE_BLOCK_OUT)):
+        for j in range(3):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+        if i < 3:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
+        prev = cout
+    norm("decoder.conv_norm_out", VAE_BLOCK_OUT[0]); conv("decoder.conv_out", VAE_BLOCK_OUT[0], 3, 3)
+    return out

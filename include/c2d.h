@@ -131,6 +131,29 @@ int c2d_cfg_sched_step(const void* eps2, float* x, void* xin2, float* trace, int
 int c2d_softmax_rows(const void* x, void* y, int M, int N, float scale, int dtype, void* stream);
 int c2d_transpose(const void* x, void* y, int batch, int R, int C, int dtype, void* stream);
 
+/* ---- audio-conditioning side (once per image; latency-bound small kernels) ---------------------- */
+/* y[b,k,:] = a + b with per-operand broadcast: mode 0 = [B,K,D], 1 = [B,1,D], 2 = [1,K,D].
+ * (token offsets / positional tables: models/hierarchical_audio_v4.py:205,479-480,490; audio_adapter_v4.py:91-93,108) */
+int c2d_bcast_add(const void* a, const void* b, void* y, int B, int K, int D, int a_mode, int b_mode, int dtype,
+                  void* stream);
+/* SoftHierarchicalDecomposition.compute_assignments (models/hierarchical_audio_v4.py:154-182):
+ * assign[r,:] = softmax((10 cos(tok_r, anchor_l) + W2 gelu(W1 tok_r + b1) + b2) / T); tokens [rows][D],
+ * anchors [L][D], w1 [Hg][D], w2 [L][Hg], temperature: device fp32 scalar, assign fp32 [rows][L]. */
+int c2d_hier_assign(const void* tokens, const void* anchors, const void* w1, const float* b1, const void* w2,
+                    const float* b2, const float* temperature, float* assign, int rows, int D, int L, int Hg,
+                    int dtype, void* stream);
+/* LevelToUNetRouter.forward (models/hierarchical_audio_v4.py:325-369), 3 levels -> early/mid/late.
+ * hw (fp32 [B][3]) may be NULL (no adaptive weights); routing fp32 [3][3]; gates fp32 {early,mid,late}. */
+int c2d_hier_route(const void* tok10, const float* assign, const float* hw, const float* routing, const float* gates,
+                   void* r_early, void* r_mid, void* r_late, int B, int K, int D, int dtype, void* stream);
+/* apply_normalization (scripts/inference.py:92-99): y = x * target / mean(||x||_2); per_sample = 0 is the
+ * reference's batch-coupled mean, per_sample = 1 the sharding-invariant variant (SURVEY decision D3). */
+int c2d_norm_scale(const void* x, void* y, int B, int K, int D, float target, int per_sample, int dtype, void* stream);
+/* HierarchicalAudioDecomposition (legacy 5-3-2, models/hierarchical_audio_v4.py:849-864):
+ * out[B][nf+nb+na][D] = cat(fg * w0, bg * w1, amb * w2), w = softmax(hierarchy_weights[3]). */
+int c2d_legacy_combine(const void* fg, const void* bg, const void* amb, const float* hierarchy_weights, void* out,
+                       int B, int nf, int nb, int na, int D, int dtype, void* stream);
+
 /* ---- weight packing helpers (run once at load time) ------------------------------------------ */
 /* [Cout][Cin][3][3] fp32 (PyTorch/diffusers layout) -> [Cout][3][3][Cin] dtype */
 int c2d_pack_conv3x3(const float* w, void* out, int Cout, int Cin, int dtype, void* stream);

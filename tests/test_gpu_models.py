@@ -1,0 +1,114 @@
+"""Drop-in modules on the GPU through the C ABI vs the golden vectors generated from the UNMODIFIED
+reference modules (-m gpu).  fp32: <= 1e-5 rel-L2; bf16 activations: <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio as A
+from oracle.pipeline import np_randn, rel_l2, to_torch
+from oracle.weights import synth_state_dict
+
+from clap2diffusion_b200 import ops
+from clap2diffusion_b200.models import audio_adapter_v4 as padapter
+from clap2diffusion_b200.models import audio_attention_processor as pproc
+from clap2diffusion_b200.models import hierarchical_audio_v4 as phier
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _load(mod, sd):
+    mod.load_state_dict(to_torch(sd))
+    return mod.to(DEV).eval()
+
+
+def test_audio_adapter(gold):
+    g = gold("audio_adapter.npz")
+    m = _load(padapter.AudioAdapter(), synth_state_dict(A.audio_adapter_spec(), int(g["seed"])))
+    with torch.no_grad():
+        out = m(_t(g["clap"]).to(DEV))
+        assert rel_l2(out, _t(g["tokens"])) < 1e-5
+        assert rel_l2(ops.norm_scale(out, 60.0, False), _t(g["tokens_norm60"])) < 1e-5
+        # batch-256 (config 4 size) agrees with batch-3 rows
+        big = m(_t(g["clap"]).to(DEV).repeat(86, 1)[:256])
+        assert rel_l2(big[:3], _t(g["tokens"])) < 1e-5
+
+
+def test_improved_hier(gold):
+    g = gold("improved_hier.npz")
+    sd = synth_state_dict(A.improved_hier_spec(), int(g["seed"]))
+    for k, v in A.IMPROVED_BUFFERS.items():
+        sd[k] = np.asarray(v, dtype=np.float32)
+    m = _load(phier.ImprovedHierarchicalAudioEncoder(), sd)
+    with torch.no_grad():
+        t77, info = m(_t(g["clap"]).to(DEV), return_all=True)
+    assert rel_l2(t77, _t(g["tokens_77"])) < 1e-5
+    for k in ("tokens_10", "assignments", "hierarchy_weights"):
+        assert rel_l2(info[k], _t(g[k])) < 1e-5, k
+    for lvl in ("early", "mid", "late"):
+        assert rel_l2(info["routed"][lvl], _t(g[f"routed_{lvl}"])) < 1e-5
+    m.decomposer.set_temperature(0.5)
+    with torch.no_grad():
+        enc = m.encode(_t(g["clap"]).to(DEV))
+    assert rel_l2(enc["assignments"], _t(g["assignments_T05"])) < 1e-5
+
+
+def test_legacy_hier(gold):
+    g = gold("legacy_hier.npz")
+    m = _load(phier.HierarchicalAudioV4(), synth_state_dict(A.legacy_hier_spec(), int(g["seed"])))
+    with torch.no_grad():
+        t77, hz = m(_t(g["clap"]).to(DEV), return_intermediate=True)
+    assert rel_l2(t77, _t(g["tokens_77"])) < 1e-5
+    for k in ("tokens10", "foreground", "background", "ambience", "weights"):
+        assert rel_l2(hz[k], _t(g[k])) < 1e-5, k
+
+
+class _Site:
+    spatial_norm = None
+    norm_cross = None
+    residual_connection = False
+    rescale_output_factor = 1.0
+
+    def __init__(self, sd, heads=8):
+        lin = lambda w, b=None: type("L", (), {"weight": w, "bias": b})()
+        self.to_q, self.to_k, self.to_v = lin(sd["to_q.weight"]), lin(sd["to_k.weight"]), lin(sd["to_v.weight"])
+        self.to_out = [lin(sd["to_out.0.weight"], sd["to_out.0.bias"])]
+        self.heads = heads
+        self.scale = (sd["to_q.weight"].shape[0] // heads) ** -0.5
+
+
+@pytest.mark.parametrize("N,C", [(4096, 320), (1024, 640), (256, 1280), (64, 1280)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_attn_processor_sites(gold, N, C, dtype, tol):
+    g = gold("attn_processor.npz")
+    seed = int(g["seed"])
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    ehs = _t(np_randn("ehs", (2, 77, 768))).to(DEV)
+    audio = (_t(np_randn("audio10", (2, 10, 768))) * 0.3).to(DEV)
+    asd = synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.")
+    site = _Site({k.split(".", 1)[1]: torch.from_numpy(v).to(DEV) for k, v in asd.items()})
+    h = _t(np_randn(f"h_{N}_{C}", (2, N, C))).to(DEV).to(dtype)
+    rows = torch.from_numpy(g[f"rows_{N}_{C}"]).to(DEV)
+    for mode in ("add", "concat"):
+        proc = pproc.AudioAttnProcessor(level="mid", mode=mode)
+        proc.load_state_dict(psd)
+        proc = proc.to(DEV).eval()
+        with torch.no_grad():
+            out = proc(site, h, encoder_hidden_states=ehs, audio={"mid": audio})
+            out_na = proc(site, h, encoder_hidden_states=ehs)
+        assert out.dtype == dtype and tuple(out.shape) == (2, N, C)
+        assert rel_l2(out[:, rows].float(), _t(g[f"out_{mode}_{N}_{C}"])) < tol, mode
+        assert rel_l2(out_na[:, rows].float(), _t(g[f"out_noaudio_{N}_{C}"])) < tol
+
+
+def test_gated_xattn(gold):
+    g = gold("gated_xattn.npz")
+    m = _load(padapter.AudioCrossAttention(320), synth_state_dict(A.gated_xattn_spec(320), int(g["seed"])))
+    h, a = _t(np_randn("gx_h", (2, 256, 320))).to(DEV), _t(np_randn("gx_a16", (2, 16, 768))).to(DEV)
+    with torch.no_grad():
+        assert rel_l2(m(h, a), _t(g["out"])) < 1e-5
+        assert rel_l2(m(h, a, _t(g["mask"]).to(DEV)), _t(g["out_masked"])) < 1e-5

@@ -1,0 +1,267 @@
+"""Kernel-level parity (-m gpu): every libc2d entry point, called through the C ABI (ctypes), against a plain
+PyTorch fp32 evaluation of the same op (tests/torch_ops.py) on identical inputs.
+Tolerances: fp32 kernels 2e-5 rel-L2 (summation order only); bf16 kernels 1e-2 (inputs are rounded to bf16
+first, so the only differences are fp32-accumulate order and the final bf16 rounding)."""
+import numpy as np
+import pytest
+import torch
+
+import torch_ops as T
+from clap2diffusion_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, dtype=F32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(hash((shape, seed)) % (2 ** 31))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def tol(dtype):
+    return 2e-5 if dtype == F32 else 1e-2
+
+
+# ------------------------------------------------------------------ linear
+LIN_CASES = [
+    # M, N, K, impl, dtype
+    (300, 200, 96, ops.IMPL_SIMT, F32), (5, 24576, 256, ops.IMPL_SIMT, F32), (77, 3, 6, ops.IMPL_SIMT, F32),
+    (130, 70, 36, ops.IMPL_SIMT, F32), (256, 320, 320, ops.IMPL_SIMT, BF16),
+    (8192, 320, 320, ops.IMPL_TCGEN05, BF16), (2048, 640, 2560, ops.IMPL_TCGEN05, BF16),
+    (512, 1280, 1280, ops.IMPL_TCGEN05, BF16), (128, 1280, 5120, ops.IMPL_TCGEN05, BF16),
+    (1000, 200, 72, ops.IMPL_TCGEN05, BF16), (154, 1536, 768, ops.IMPL_TCGEN05, BF16),
+    (4096, 4096, 512, ops.IMPL_TCGEN05, BF16), (64, 8, 64, ops.IMPL_TCGEN05, BF16),
+]
+
+
+@pytest.mark.parametrize("M,N,K,impl,dtype", LIN_CASES)
+def test_linear(M, N, K, impl, dtype):
+    x, w = rnd(M, K, dtype=dtype), rnd(N, K, dtype=dtype, scale=K ** -0.5, seed=1)
+    b, r = rnd(N, seed=2), rnd(M, N, dtype=dtype, seed=3)
+    for act in (ops.ACT_NONE, ops.ACT_GELU, ops.ACT_SILU):
+        y = ops.linear(x, w, b, act=act, residual=r, impl=impl)
+        assert rel(y, T.linear(x, w, b, act=act, residual=r)) < tol(dtype), (act,)
+    y = ops.linear(x, w, impl=impl)
+    assert rel(y, T.linear(x, w)) < tol(dtype)
+
+
+@pytest.mark.parametrize("impl,dtype", [(ops.IMPL_SIMT, F32), (ops.IMPL_TCGEN05, BF16)])
+def test_linear_strided_and_rowvec(impl, dtype):
+    B, N_, C = 2, 256, 320
+    qkv = rnd(B, N_, 3 * C, dtype=dtype)
+    w = rnd(C, C, dtype=dtype, scale=C ** -0.5, seed=1)
+    x = qkv[..., C:2 * C]                       # strided rows (ldx = 3C)
+    y = ops.linear(x, w, impl=impl)
+    assert rel(y, T.linear(x, w)) < tol(dtype)
+    out = torch.zeros(B, N_, 2 * C, device=DEV, dtype=dtype)
+    ops.linear(x, w, out=out[..., C:], impl=impl)                                   # strided output (ldy = 2C)
+    assert rel(out[..., C:], T.linear(x, w)) < tol(dtype) and float(out[..., :C].abs().max()) == 0.0
+    rv = rnd(B, C, seed=5)
+    y = ops.linear(x, w, rowvec=rv, rows_per_vec=N_, impl=impl)
+    assert rel(y, T.linear(x, w, rowvec=rv, rows_per_vec=N_)) < tol(dtype)
+
+
+def test_geglu_fused_vs_unfused():
+    M, C = 1024, 320
+    x = rnd(M, C, dtype=BF16)
+    w, b = rnd(8 * C, C, scale=C ** -0.5, seed=1), rnd(8 * C, seed=2, scale=0.1)
+    wp, bp = ops.pack_geglu(w, b, BF16)
+    wp_ref, bp_ref = T.pack_geglu(w, b, BF16)
+    assert torch.equal(wp, wp_ref) and torch.equal(bp, bp_ref)
+    y = ops.geglu_linear(x, wp, bp)
+    ref = T.geglu(T.linear(x.float(), w.to(BF16).float(), b))
+    assert rel(y, ref) < 1e-2
+    y32 = ops.geglu(ops.linear(x.float(), w, b, impl=ops.IMPL_SIMT))
+    assert rel(y32, T.geglu(T.linear(x.float(), w, b))) < 2e-5
+
+
+# ------------------------------------------------------------------ conv3x3
+CONV_SIMT = [(2, 16, 16, 4, 320, 1, False), (1, 16, 16, 64, 96, 2, False), (2, 8, 8, 128, 64, 1, True),
+             (1, 9, 7, 24, 40, 1, False), (1, 9, 7, 24, 40, 2, False)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,up", CONV_SIMT)
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_conv3x3_simt(B, H, W, Cin, Cout, stride, up, dtype):
+    x = rnd(B, H, W, Cin, dtype=dtype)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), dtype)
+    b = rnd(Cout, seed=2)
+    y = ops.conv3x3(x, w, b, stride=stride, upsample=up, impl=ops.IMPL_SIMT)
+    ref = T.conv3x3(x, w, b, stride=stride, upsample=up)
+    assert y.shape == ref.shape
+    assert rel(y, ref) < tol(dtype)
+
+
+CONV_TC = [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (2, 16, 16, 1280, 1280), (2, 8, 8, 1280, 1280),
+           (3, 8, 8, 2560, 1280), (1, 32, 32, 960, 640), (1, 64, 64, 320, 4), (1, 128, 128, 128, 128),
+           (1, 256, 256, 64, 64), (5, 4, 4, 64, 32), (1, 16, 16, 72, 48)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_TC)
+def test_conv3x3_tcgen05(B, H, W, Cin, Cout):
+    x = rnd(B, H, W, Cin, dtype=BF16)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), BF16)
+    b, rv, r = rnd(Cout, seed=2), rnd(B, Cout, seed=3), rnd(B, H, W, Cout, dtype=BF16, seed=4)
+    y = ops.conv3x3(x, w, b, rowvec=rv, residual=r, impl=ops.IMPL_TCGEN05)
+    assert rel(y, T.conv3x3(x, w, b, rowvec=rv, residual=r)) < 1e-2
+    y2 = ops.conv3x3(x, w, b, impl=ops.IMPL_TCGEN05)
+    ys = ops.conv3x3(x, w, b, impl=ops.IMPL_SIMT)
+    assert rel(y2, T.conv3x3(x, w, b)) < 1e-2
+    assert rel(y2, ys) < 1e-2            # tcgen05 vs FFMA on identical bf16 inputs
+
+
+def test_pack_conv():
+    w = rnd(24, 16, 3, 3)
+    assert torch.equal(ops.pack_conv3x3(w, F32), T.pack_conv3x3(w, F32))
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("B,HW,C", [(2, 4096, 320), (2, 64, 1280), (3, 256, 2560), (1, 1024, 1920), (1, 16384, 128)])
+def test_group_norm(B, HW, C, dtype):
+    x = rnd(B, HW, C, dtype=dtype) * 2 + 0.5
+    g, b = 1 + 0.1 * rnd(C, seed=1), 0.1 * rnd(C, seed=2)
+    for silu in (False, True):
+        y = ops.group_norm(x, g, b, 32, 1e-5, silu)
+        assert rel(y, T.group_norm(x, g, b, 32, 1e-5, silu)) < (5e-5 if dtype == F32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_group_norm_two_source(dtype):
+    B, HW, C1, C2 = 2, 1024, 640, 320
+    x1, x2 = rnd(B, HW, C1, dtype=dtype), rnd(B, HW, C2, dtype=dtype, seed=7) * 3
+    g, b = 1 + 0.1 * rnd(C1 + C2, seed=1), 0.1 * rnd(C1 + C2, seed=2)
+    raw = torch.empty(B, HW, C1 + C2, device=DEV, dtype=dtype)
+    y = ops.group_norm(x1, g, b, 32, 1e-5, True, x2=x2, raw_cat=raw)
+    assert torch.equal(raw, torch.cat([x1, x2], -1))
+    assert rel(y, T.group_norm(x1, g, b, 32, 1e-5, True, x2=x2)) < (5e-5 if dtype == F32 else 1e-2)
+    assert torch.equal(ops.concat(x1, x2), torch.cat([x1, x2], -1))
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("M,C", [(8192, 320), (300, 1280), (77, 768), (5, 6), (33, 192)])
+def test_layer_norm(M, C, dtype):
+    x = rnd(M, C, dtype=dtype) * 3 + 1
+    g, b = 1 + 0.1 * rnd(C, seed=1), 0.1 * rnd(C, seed=2)
+    assert rel(ops.layer_norm(x, g, b, 1e-5), T.layer_norm(x, g, b, 1e-5)) < (2e-5 if dtype == F32 else 1e-2)
+
+
+# ------------------------------------------------------------------ attention
+ATT = [(2, 8, 1024, 1024, 40), (1, 8, 256, 256, 160), (2, 8, 64, 64, 160), (2, 8, 1024, 77, 80), (2, 8, 300, 81, 40),
+       (3, 4, 10, 10, 48), (2, 8, 77, 10, 32), (2, 8, 16, 16, 96), (2, 8, 256, 16, 64)]
+
+
+@pytest.mark.parametrize("B,h,Nq,Nkv,d", ATT)
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_attention_simt(B, h, Nq, Nkv, d, dtype):
+    q, k, v = rnd(B, Nq, h * d, dtype=dtype), rnd(B, Nkv, h * d, dtype=dtype, seed=1), rnd(B, Nkv, h * d, dtype=dtype, seed=2)
+    o = ops.attention(q, k, v, h, impl=ops.IMPL_SIMT)
+    assert rel(o, T.attention(q, k, v, h)) < (2e-5 if dtype == F32 else 1e-2)
+
+
+def test_attention_packed_views_mask_and_small():
+    B, N_, C, h = 2, 256, 320, 8
+    qkv = rnd(B, N_, 3 * C)
+    o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], h, impl=ops.IMPL_SIMT)
+    assert rel(o, T.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], h)) < 2e-5
+    # key-padding mask (AudioCrossAttention semantics)
+    q, k, v = rnd(B, 64, 512), rnd(B, 16, 512, seed=1), rnd(B, 16, 512, seed=2)
+    mask = torch.ones(B, 16, dtype=torch.bool, device=DEV)
+    mask[:, 12:] = False
+    assert rel(ops.attention(q, k, v, 8, mask=mask), T.attention(q, k, v, 8, mask=mask)) < 2e-5
+    # single head d = 768 with batch-broadcast queries (AudioTokenGenerator)
+    q0 = rnd(1, 16, 768)
+    kv = rnd(B, 16, 2, 768, seed=3)
+    o = ops.attention(q0.expand(B, 16, 768), kv[:, :, 0], kv[:, :, 1], 1)
+    assert rel(o, T.attention(q0.expand(B, 16, 768), kv[:, :, 0], kv[:, :, 1], 1)) < 2e-5
+
+
+# ------------------------------------------------------------------ audio context + small kernels
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("mode", [ops.AUDIO_ADD, ops.AUDIO_CONCAT])
+@pytest.mark.parametrize("K", [10, 16, 3])
+def test_audio_context(dtype, mode, K):
+    B = 2
+    ehs, audio = rnd(B, 77, 768, dtype=dtype), rnd(B, K, 768, dtype=dtype, seed=1) * 0.3
+    w1, b1 = rnd(64, 768, dtype=dtype, scale=768 ** -0.5, seed=2), rnd(64, seed=3, scale=0.1)
+    w2, b2 = rnd(768, 64, dtype=dtype, scale=0.125, seed=4), rnd(768, seed=5, scale=0.1)
+    alpha = torch.tensor([0.3], device=DEV)
+    y = ops.audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode)
+    ref = T.audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode)
+    assert y.shape == ref.shape and rel(y, ref) < (1e-5 if dtype == F32 else 1e-2)
+
+
+def test_elementwise_and_layout():
+    t = torch.tensor([981.0, 1.0, 500.0], device=DEV)
+    assert rel(ops.timestep_embedding(t, 320), T.timestep_embedding(t, 320)) < 2e-6
+    x = rnd(3, 1000, 640)
+    assert rel(ops.geglu(x), T.geglu(x)) < 1e-6
+    assert rel(ops.unary(x, ops.ACT_SILU), T.unary(x, 2)) < 1e-6
+    assert torch.equal(ops.cast(x, BF16), x.to(BF16))
+    assert rel(ops.add(x, x * 2), x * 3) < 1e-7
+    y = rnd(2, 8, 16, 64)
+    assert torch.equal(ops.upsample2x(y), T.upsample2x(y))
+    z = rnd(2, 4, 16, 24)
+    nh = ops.nchw_to_nhwc(z, F32)
+    assert torch.equal(nh, z.permute(0, 2, 3, 1).contiguous()) and torch.equal(ops.nhwc_to_nchw(nh), z)
+    m = rnd(5, 37, 91)
+    assert torch.equal(ops.transpose(m), m.transpose(1, 2).contiguous())
+    s = rnd(300, 4096)
+    assert rel(ops.softmax_rows(s, 0.044), T.softmax_rows(s, 0.044)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_cfg_sched_step(dtype):
+    B, H, W = 3, 16, 16
+    eps2 = rnd(2 * B, H, W, 4, dtype=dtype)
+    x = rnd(B, 4, H, W, seed=1)
+    coef = torch.tensor([0.97, -0.12, 0.8], device=DEV)
+    x_ref, xin_ref = x.clone(), torch.empty(2 * B, H, W, 4, device=DEV, dtype=dtype)
+    T.cfg_sched_step(eps2, x_ref, xin_ref, 7.5, coef)
+    xin, tr = torch.empty_like(xin_ref), torch.empty_like(x)
+    ops.cfg_sched_step(eps2, x, xin, 7.5, coef, trace=tr)
+    assert rel(x, x_ref) < 1e-6 and torch.equal(tr, x) and rel(xin, xin_ref) < (1e-6 if dtype == F32 else 5e-3)
+
+
+def test_audio_small_kernels():
+    B, K, D = 3, 10, 768
+    a, b = rnd(B, D), rnd(K, D, seed=1)
+    assert rel(ops.bcast_add(a, b, B, K, D, 1, 2), T.bcast_add(a, b, B, K, D, 1, 2)) < 1e-7
+    tok = rnd(B, K, D)
+    anchors, w1, b1, w2, b2 = rnd(3, D, scale=0.02, seed=2), rnd(10, D, scale=0.03, seed=3), rnd(10, seed=4), rnd(3, 10, seed=5), rnd(3, seed=6)
+    temp = torch.tensor(2.0, device=DEV)
+    asg = ops.hier_assign(tok, anchors, w1, b1, w2, b2, temp.reshape(1))
+    assert rel(asg, T.hier_assign(tok, anchors, w1, b1, w2, b2, temp)) < 1e-5
+    hw = torch.softmax(rnd(B, 3, seed=7), -1)
+    routing, gates = rnd(3, 3, seed=8), rnd(3, seed=9)
+    for got, want in zip(ops.hier_route(tok, asg, hw, routing, gates), T.hier_route(tok, asg, hw, routing, gates)):
+        assert rel(got, want) < 1e-5
+    for per_sample in (False, True):
+        assert rel(ops.norm_scale(tok, 60.0, per_sample), T.norm_scale(tok, 60.0, per_sample)) < 1e-5
+    fg, bg, am = rnd(B, 5 * D), rnd(B, 3 * D, seed=1), rnd(B, 2 * D, seed=2)
+    hwts = torch.tensor([0.5, 0.3, 0.2], device=DEV)
+    assert rel(ops.legacy_combine(fg, bg, am, hwts, D), T.legacy_combine(fg, bg, am, hwts, D)) < 1e-6
+
+
+def test_errors_are_loud():
+    from clap2diffusion_b200._lib import C2DError
+    x = rnd(4, 8)
+    with pytest.raises(C2DError):
+        ops.linear(x.cpu(), x.cpu())
+    with pytest.raises(C2DError):   # tcgen05 path cannot take fp32
+        ops.linear(x, rnd(8, 8), impl=ops.IMPL_TCGEN05)
+    with pytest.raises(C2DError):
+        ops.conv3x3(rnd(1, 7, 7, 8, dtype=BF16), rnd(8, 3, 3, 8, dtype=BF16), impl=ops.IMPL_TCGEN05)

@@ -1,0 +1,116 @@
+"""End-to-end parity on the GPU (-m gpu): the product (libc2d kernels through the C ABI) vs the oracle on
+identical synthetic weights, audio stand-in and fixed noise.
+Gates (BASELINE.json north_star): per-step latent rel-L2 <= 1e-4 in fp32 mode, <= 1e-2 in bf16; decoded
+image PSNR >= 40 dB in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio as A
+from oracle import pipeline as PL
+from oracle import sd15
+from oracle.pipeline import psnr, rel_l2
+
+from clap2diffusion_b200.pipeline import AudioToImagePipeline
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def W():
+    return PL.build_weights(seed=0, with_vae=True)
+
+
+def _pipe(W, dtype, **kw):
+    return AudioToImagePipeline(W["unet"], W["vae"], W["hier"], {l: W[f"proc_{l}"] for l in PL.LEVELS}, W["adapter"],
+                                device=DEV, dtype=dtype, **kw)
+
+
+@pytest.fixture(scope="module")
+def pipe32(W):
+    return _pipe(W, torch.float32)
+
+
+@pytest.fixture(scope="module")
+def pipe16(W):
+    return _pipe(W, torch.bfloat16)
+
+
+def _inputs():
+    return (PL.clap_embedding(0)[None], PL.text_states("a beach")[None], PL.text_states("")[None], PL.init_noise(0)[None])
+
+
+def test_unet_forward_16x16(gold, W, pipe32, pipe16):
+    g = gold("unet_16x16.npz")
+    clap = _t(PL.clap_embedding(0))[None].to(DEV)
+    x = _t(PL.init_noise(5, 16, 16))[None].to(DEV)
+    ctx = _t(PL.text_states("a beach"))[None].to(DEV)
+    for pipe, tol in ((pipe32, 1e-4), (pipe16, 3e-2)):
+        with torch.no_grad():
+            routed = pipe.hier.encode(clap, with_tokens77=False)["routed"]
+            taps = {}
+            eps = pipe.unet(x, float(g["t"]), ctx, cross_attention_kwargs={"audio": routed}, taps=taps)
+        assert rel_l2(taps["conv_in"].float().permute(0, 3, 1, 2), _t(g["conv_in"])) < tol
+        assert rel_l2(taps["mid"].float().permute(0, 3, 1, 2), _t(g["mid"])) < tol
+        assert rel_l2(eps, _t(g["eps"])) < tol, pipe.dtype
+
+
+def test_config1_fp32_per_step_latents_and_psnr(gold, pipe32):
+    """Config 1: batch 1, 20 DDIM steps, CFG 7.5, fp32 -- every step's latent vs the CPU oracle's."""
+    g = gold("pipeline_cfg1_20steps.npz")
+    out = pipe32.generate(*_inputs(), steps=20, guidance=7.5, decode=True, trace=True)
+    errs = [rel_l2(_t(out["trace"][i]), _t(g["latents"][i:i + 1])) for i in range(20)]
+    print("fp32 per-step rel-L2:", ["%.1e" % e for e in errs])
+    assert max(errs) <= 1e-4, errs
+    p = psnr(_t(out["image"]), _t(g["image"].astype(np.float32)))
+    print("fp32 decoded-image PSNR vs oracle: %.1f dB" % p)
+    assert p >= 40.0
+
+
+def test_config1_bf16_per_step_latents(gold, pipe16):
+    g = gold("pipeline_cfg1_20steps.npz")
+    out = pipe16.generate(*_inputs(), steps=20, guidance=7.5, decode=True, trace=True)
+    errs = [rel_l2(_t(out["trace"][i]), _t(g["latents"][i:i + 1])) for i in range(20)]
+    print("bf16 per-step rel-L2:", ["%.1e" % e for e in errs])
+    print("bf16 decoded-image PSNR vs oracle: %.1f dB" % psnr(_t(out["image"]), _t(g["image"].astype(np.float32))))
+    assert max(errs) <= 1e-2, errs
+
+
+def test_config2_first_steps_and_graph_equals_eager(gold, W, pipe32, pipe16):
+    g = gold("pipeline_cfg2_first6.npz")
+    out = pipe32.generate(*_inputs(), steps=50, guidance=7.5, decode=False, trace=True, max_steps=6)
+    for i in range(6):
+        assert rel_l2(_t(out["trace"][i]), _t(g["latents"][i:i + 1])) <= 1e-4, i
+    out16 = pipe16.generate(*_inputs(), steps=50, guidance=7.5, decode=False, trace=True, max_steps=6)
+    for i in range(6):
+        assert rel_l2(_t(out16["trace"][i]), _t(g["latents"][i:i + 1])) <= 1e-2, i
+    # CUDA-graph replay must be bit-identical to eager launches of the same kernels
+    eager = _pipe(W, torch.bfloat16, use_graph=False)
+    oute = eager.generate(*_inputs(), steps=50, guidance=7.5, decode=False, trace=True, max_steps=6)
+    for i in range(6):
+        assert np.array_equal(oute["trace"][i], out16["trace"][i]), i
+
+
+def test_batch_invariance_and_euler(W, pipe16):
+    """Data-parallel invariance: an image's latents do not depend on what else is in its micro-batch."""
+    seeds, prompts = [3, 4, 5], ["a beach", "a city", "a forest"]
+    clap = np.stack([PL.clap_embedding(s) for s in seeds])
+    cc = np.stack([PL.text_states(p) for p in prompts])
+    cu = np.stack([PL.text_states("")] * 3)
+    nz = np.stack([PL.init_noise(s) for s in seeds])
+    full = pipe16.generate(clap, cc, cu, nz, steps=50, decode=False, max_steps=3)["latents"]
+    for i in range(3):
+        one = pipe16.generate(clap[i:i + 1], cc[i:i + 1], cu[i:i + 1], nz[i:i + 1], steps=50, decode=False, max_steps=3)["latents"]
+        assert rel_l2(_t(one), _t(full[i:i + 1])) < 2e-3, i
+    # Euler scheduler against the oracle (fp32 oracle on the GPU as the checker)
+    Wg = {k: {n: t.to(DEV) for n, t in v.items()} for k, v in W.items() if k != "vae" and k != "adapter"}
+    ref = PL.sample(Wg, _t(clap[:1]).to(DEV), _t(cc[:1]).to(DEV), _t(cu[:1]).to(DEV), _t(nz[:1]).to(DEV), steps=50,
+                    scheduler="euler", max_steps=2)
+    got = pipe16.generate(clap[:1], cc[:1], cu[:1], nz[:1], steps=50, scheduler="euler", decode=False, trace=True, max_steps=2)
+    for i in range(2):
+        assert rel_l2(_t(got["trace"][i]), ref["latents"][i]) <= 1e-2

@@ -1,0 +1,237 @@
+"""HOST logic of the product (weight packing, topology, skip wiring, hoisting, processor protocol, drop-in
+module plumbing, sampler, schedulers) checked on CPU against the oracle and the reference-generated golden
+vectors, with the libc2d-backed ops swapped for the torch test double (tests/torch_ops.py).  The CUDA
+kernels themselves are checked by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+import torch_ops
+from oracle import audio as A
+from oracle import pipeline as PL
+from oracle import sd15
+from oracle.pipeline import np_randn, rel_l2, to_torch
+from oracle.weights import synth_state_dict
+
+from clap2diffusion_b200 import schedulers
+from clap2diffusion_b200.models import audio_adapter_v4 as padapter
+from clap2diffusion_b200.models import audio_attention_processor as pproc
+from clap2diffusion_b200.models import hierarchical_audio_v4 as phier
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def W():
+    return PL.build_weights(seed=0, with_vae=True)
+
+
+def test_state_dict_contract():
+    """Same keys and shapes as the reference modules, via the oracle specs."""
+    for mod, spec, extra in ((padapter.AudioAdapter(), A.audio_adapter_spec(), {}),
+                             (phier.ImprovedHierarchicalAudioEncoder(), A.improved_hier_spec(), A.IMPROVED_BUFFERS),
+                             (phier.HierarchicalAudioV4(), A.legacy_hier_spec(), {}),
+                             (pproc.AudioAttnProcessor("mid"), A.attn_processor_spec(), {}),
+                             (padapter.AudioCrossAttention(320), A.gated_xattn_spec(320), {})):
+        sd = mod.state_dict()
+        want = {p.name: tuple(p.shape) for p in spec}
+        want.update({k: tuple(np.asarray(v).shape) for k, v in extra.items()})
+        assert {k: tuple(v.shape) for k, v in sd.items()} == want, type(mod).__name__
+
+
+def test_default_init_statistics():
+    """KAT (iv): tokens out of the default-init adapter have norm ~ sqrt(768); gates at their reference init."""
+    m = padapter.AudioCrossAttention(320)
+    assert abs(float(m.gate) + 5.0) < 1e-6
+    r = phier.LevelToUNetRouter()
+    assert torch.allclose(r.routing_matrix.detach(), torch.tensor([[.1, .3, .6], [.2, .6, .2], [.6, .3, .1]]))
+    assert float(pproc.AudioAttnProcessor("early").alpha) == 0.0
+
+
+def test_temperature_scheduler(gold):
+    g = gold("temperature_kat.npz")
+    dec = phier.SoftHierarchicalDecomposition()
+    sch = phier.TemperatureScheduler(dec, T_max=2.0, T_min=0.5, total_steps=2000)
+    for step, temp in zip(g["steps"].tolist(), g["temps"].tolist()):
+        sch.step(step)
+        assert abs(float(dec.temperature) - temp) < 1e-6
+    with pytest.raises(ValueError):
+        phier.TemperatureScheduler(dec, mode="bogus").step(300)
+    with pytest.raises(ValueError):
+        phier.CrossHierarchyAttention(768, num_heads=4, bottleneck_dim=190)
+
+
+def test_audio_adapter_module(gold):
+    g = gold("audio_adapter.npz")
+    m = padapter.AudioAdapter().eval()
+    m.load_state_dict(to_torch(synth_state_dict(A.audio_adapter_spec(), int(g["seed"]))))
+    with torch_ops.installed(), torch.no_grad():
+        out = m(_t(g["clap"]))
+        n60 = torch_ops.norm_scale(out, 60.0, False)
+    assert rel_l2(out, _t(g["tokens"])) < 5e-6
+    assert rel_l2(n60, _t(g["tokens_norm60"])) < 5e-6
+
+
+def test_improved_hier_module(gold):
+    g = gold("improved_hier.npz")
+    sd = synth_state_dict(A.improved_hier_spec(), int(g["seed"]))
+    for k, v in A.IMPROVED_BUFFERS.items():
+        sd[k] = np.asarray(v, dtype=np.float32)
+    m = phier.ImprovedHierarchicalAudioEncoder().eval()
+    m.load_state_dict(to_torch(sd))
+    with torch_ops.installed(), torch.no_grad():
+        t77, info = m(_t(g["clap"]), return_all=True)
+        t77b = m(_t(g["clap"]))
+    assert rel_l2(t77, _t(g["tokens_77"])) < 5e-6 and rel_l2(t77b, _t(g["tokens_77"])) < 5e-6
+    assert rel_l2(info["tokens_10"], _t(g["tokens_10"])) < 5e-6
+    assert rel_l2(info["assignments"], _t(g["assignments"])) < 5e-6
+    assert rel_l2(info["hierarchy_weights"], _t(g["hierarchy_weights"])) < 5e-6
+    for lvl in ("early", "mid", "late"):
+        assert rel_l2(info["routed"][lvl], _t(g[f"routed_{lvl}"])) < 5e-6
+    assert set(info["losses"]) == {"entropy", "orthogonality", "prior"}
+    assert set(info["stats"]) == {"avg_assignment", "entropy", "effective_levels"}
+    assert info["temperature"] == 2.0
+
+
+def test_legacy_hier_module(gold):
+    g = gold("legacy_hier.npz")
+    m = phier.HierarchicalAudioV4().eval()
+    m.load_state_dict(to_torch(synth_state_dict(A.legacy_hier_spec(), int(g["seed"]))))
+    with torch_ops.installed(), torch.no_grad():
+        t77, hz = m(_t(g["clap"]), return_intermediate=True)
+    assert rel_l2(t77, _t(g["tokens_77"])) < 5e-6
+    for k in ("tokens10", "foreground", "background", "ambience", "weights"):
+        assert rel_l2(hz[k], _t(g[k])) < 5e-6, k
+    assert tuple(hz["foreground"].shape) == (3, 5, 768) and tuple(hz["ambience"].shape) == (3, 2, 768)
+
+
+class _Site:
+    """Duck-typed diffusers Attention (what the processor reads)."""
+    spatial_norm = None
+    norm_cross = None
+    residual_connection = False
+    rescale_output_factor = 1.0
+
+    def __init__(self, sd, heads=8):
+        lin = lambda w, b=None: type("L", (), {"weight": w, "bias": b})()
+        self.to_q, self.to_k, self.to_v = lin(sd["to_q.weight"]), lin(sd["to_k.weight"]), lin(sd["to_v.weight"])
+        self.to_out = [lin(sd["to_out.0.weight"], sd["to_out.0.bias"])]
+        self.heads = heads
+        self.scale = (sd["to_q.weight"].shape[0] // heads) ** -0.5
+
+
+def test_attn_processor_module(gold):
+    g = gold("attn_processor.npz")
+    seed = int(g["seed"])
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    ehs = _t(np_randn("ehs", (2, 77, 768)))
+    audio = _t(np_randn("audio10", (2, 10, 768))) * 0.3
+    for (N, C) in ((256, 1280), (64, 1280)):
+        asd = synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.")
+        site = _Site(to_torch({k.split(".", 1)[1]: v for k, v in asd.items()}))
+        h = _t(np_randn(f"h_{N}_{C}", (2, N, C)))
+        rows = g[f"rows_{N}_{C}"]
+        for mode in ("add", "concat"):
+            proc = pproc.AudioAttnProcessor(level="mid", mode=mode).eval()
+            proc.load_state_dict(psd)
+            with torch_ops.installed(), torch.no_grad():
+                out = proc(site, h, encoder_hidden_states=ehs, audio={"mid": audio})
+                out_na = proc(site, h, encoder_hidden_states=ehs)                 # fall-through: no audio
+                out_lv = proc(site, h, encoder_hidden_states=ehs, audio={"late": audio})   # other level only
+            assert rel_l2(out[:, rows], _t(g[f"out_{mode}_{N}_{C}"])) < 5e-6
+            assert rel_l2(out_na[:, rows], _t(g[f"out_noaudio_{N}_{C}"])) < 5e-6
+            assert rel_l2(out_lv, out_na) == 0.0
+        if N == 64:   # 4-D input path
+            proc = pproc.AudioAttnProcessor(level="mid", mode="add").eval()
+            proc.load_state_dict(psd)
+            h4 = h.transpose(1, 2).reshape(2, C, 8, 8).contiguous()
+            with torch_ops.installed(), torch.no_grad():
+                o4 = proc(site, h4, encoder_hidden_states=ehs, audio={"mid": audio})
+            assert tuple(o4.shape) == (2, C, 8, 8)
+            assert rel_l2(o4.reshape(2, C, 64).transpose(1, 2)[:, rows], _t(g[f"out_add_{N}_{C}"])) < 5e-6
+
+
+def test_gated_xattn_module(gold):
+    g = gold("gated_xattn.npz")
+    m = padapter.AudioCrossAttention(320).eval()
+    m.load_state_dict(to_torch(synth_state_dict(A.gated_xattn_spec(320), int(g["seed"]))))
+    h, a = _t(np_randn("gx_h", (2, 256, 320))), _t(np_randn("gx_a16", (2, 16, 768)))
+    with torch_ops.installed(), torch.no_grad():
+        assert rel_l2(m(h, a), _t(g["out"])) < 5e-6
+        assert rel_l2(m(h, a, _t(g["mask"])), _t(g["out_masked"])) < 5e-6
+
+
+def test_schedulers_match_oracle():
+    for n in (20, 50):
+        plan = schedulers.ddim_plan(n)
+        ref = sd15.ddim_coeffs(n)
+        assert plan.timesteps == [float(t) for t, _, _ in ref]
+        assert np.allclose(plan.coef[:, 0], [a for _, a, _ in ref], rtol=1e-6)
+        assert np.allclose(plan.coef[:, 1], [b for _, _, b in ref], rtol=1e-6)
+    ts, sig = sd15.euler_sigmas(50)
+    plan = schedulers.euler_plan(50)
+    assert plan.timesteps == ts and abs(plan.init_scale - sig[0]) < 1e-6
+    assert np.allclose(plan.coef[:, 1], np.diff(np.asarray(sig)), rtol=1e-6)
+
+
+def _build_unet(W, dtype=torch.float32):
+    from clap2diffusion_b200.unet import SD15UNet
+    unet = SD15UNet(W["unet"], device="cpu", dtype=dtype)
+    mgr = pproc.AudioProcessorManager(unet)
+    mgr.setup_processors(mode="add")
+    assert {k: len(v) for k, v in mgr.level_mapping.items()} == {"early": 4, "mid": 7, "late": 5}
+    for lvl, names in mgr.level_mapping.items():
+        unet.sites[names[0][:-len(".processor")]].processor.load_state_dict(W[f"proc_{lvl}"])
+    return unet, mgr
+
+
+def test_unet_host_logic_vs_oracle(gold, W):
+    g = gold("unet_16x16.npz")
+    clap = _t(PL.clap_embedding(0))[None]
+    with torch_ops.installed(), torch.no_grad():
+        unet, mgr = _build_unet(W)
+        assert len(unet.attn_processors) == 32
+        assert sorted(unet.attn_processors) == sorted(sd15.attn_processor_names())
+        enc = phier.ImprovedHierarchicalAudioEncoder().eval()
+        enc.load_state_dict(W["hier"])
+        routed = enc.encode(clap, with_tokens77=False)["routed"]
+        x = _t(PL.init_noise(5, 16, 16))[None]
+        taps = {}
+        eps = unet(x, float(g["t"]), _t(PL.text_states("a beach"))[None],
+                   cross_attention_kwargs=mgr.get_audio_kwargs(routed), taps=taps)
+    assert rel_l2(taps["conv_in"].permute(0, 3, 1, 2), _t(g["conv_in"])) < 1e-5
+    assert rel_l2(taps["mid"].permute(0, 3, 1, 2), _t(g["mid"])) < 1e-5
+    assert rel_l2(eps, _t(g["eps"])) < 2e-5
+
+
+def test_sampler_host_logic_vs_oracle(W):
+    """3 DDIM + 3 Euler steps with CFG on an 8x8 latent: product loop (hoisted tables, fused CFG/scheduler
+    contract, D2 audio tiling) == oracle loop."""
+    from clap2diffusion_b200.sampler import Sampler
+    clap = _t(np.stack([PL.clap_embedding(1), PL.clap_embedding(2)]))
+    cc = _t(np.stack([PL.text_states("a beach"), PL.text_states("a city")]))
+    cu = _t(np.stack([PL.text_states("")] * 2))
+    noise = _t(np.stack([PL.init_noise(1, 8, 8), PL.init_noise(2, 8, 8)]))
+    for sched in ("ddim", "euler"):
+        ref = PL.sample(W, clap, cc, cu, noise, steps=50, guidance=7.5, scheduler=sched, max_steps=3)
+        with torch_ops.installed(), torch.no_grad():
+            unet, _ = _build_unet(W)
+            enc = phier.ImprovedHierarchicalAudioEncoder().eval()
+            enc.load_state_dict(W["hier"])
+            out = Sampler(unet, enc, None, use_graph=False).sample(clap, cc, cu, noise, steps=50, guidance=7.5,
+                                                                   scheduler=sched, decode=False, trace=True, max_steps=3)
+        for i in range(3):
+            assert rel_l2(out["trace"][i], ref["latents"][i]) < 5e-5, (sched, i)
+
+
+def test_vae_host_logic_vs_oracle(W):
+    from clap2diffusion_b200.vae import VAEDecoder
+    z = _t(PL.init_noise(3, 8, 8))[None] * 0.5
+    with torch.no_grad():
+        ref = sd15.vae_decode(W["vae"], z)
+    with torch_ops.installed(), torch.no_grad():
+        img = VAEDecoder(W["vae"], device="cpu", dtype=torch.float32).decode(z)
+    assert tuple(img.shape) == (1, 3, 64, 64)
+    assert rel_l2(img, ref) < 2e-5

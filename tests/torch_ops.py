@@ -1,0 +1,221 @@
+"""TEST DOUBLE for ``clap2diffusion_b200.ops``: the same function signatures implemented with plain torch,
+so the HOST logic of the product (weight packing, topology, skip wiring, hoisting, processor protocol,
+drop-in module plumbing) can be checked against the oracle on a machine without a GPU.
+
+It is installed only by tests (``with torch_ops.installed(): ...``) and lives under tests/; the product
+never imports it and has no CPU path of its own.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+from clap2diffusion_b200 import ops as real_ops
+
+ACT = {0: lambda v: v, 1: F.gelu, 2: F.silu}
+
+
+def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1, out=None, impl=0):
+    y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
+    if rowvec is not None:
+        M = y.numel() // y.shape[-1]
+        idx = torch.arange(M, device=y.device) // rows_per_vec
+        y = (y.reshape(M, -1) + rowvec.reshape(-1, y.shape[-1])[idx]).reshape(y.shape)
+    y = ACT[act](y)
+    if residual is not None:
+        y = y + residual.float().reshape(y.shape)
+    y = y.to(x.dtype)
+    if out is not None:
+        out.copy_(y.reshape(out.shape))
+        return out
+    return y
+
+
+def pack_geglu(w, bias, dtype):
+    F2, K = w.shape
+    Fh = F2 // 2
+    idx = []
+    for blk in range(Fh // 64):
+        idx += list(range(blk * 64, blk * 64 + 64)) + list(range(Fh + blk * 64, Fh + blk * 64 + 64))
+    idx = torch.tensor(idx, device=w.device)
+    return w[idx].to(dtype).contiguous(), (None if bias is None else bias[idx].float().contiguous())
+
+
+def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=0):
+    y = F.linear(x.float(), w_packed.float(), bias_packed)
+    M = y.numel() // y.shape[-1]
+    y = y.reshape(M, -1, 2, 64)                     # blocks of (a[64], g[64])
+    r = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(*x.shape[:-1], -1)
+    return r.to(x.dtype)
+
+
+def geglu(x, *, out=None):
+    a, g = x.float().chunk(2, dim=-1)
+    return (a * F.gelu(g)).to(x.dtype)
+
+
+def pack_conv3x3(w, dtype):
+    return w.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, upsample=False, out=None, impl=0):
+    xin = x.float().permute(0, 3, 1, 2)
+    if upsample:
+        xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+    w = w_packed.float().permute(0, 3, 1, 2)
+    y = F.conv2d(xin, w, None if bias is None else bias.float(), stride=stride, padding=1)
+    if rowvec is not None:
+        y = y + rowvec.reshape(y.shape[0], -1)[:, :, None, None]
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float().reshape(y.shape)
+    return y.contiguous().to(x.dtype)
+
+
+def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_cat=None, out=None):
+    xx = x if x2 is None else torch.cat([x, x2], dim=-1)
+    if raw_cat is not None:
+        raw_cat.copy_(xx)
+    B, C = xx.shape[0], xx.shape[-1]
+    y = F.group_norm(xx.float().reshape(B, -1, C).transpose(1, 2), groups, gamma, beta, eps).transpose(1, 2)
+    if silu:
+        y = F.silu(y)
+    return y.reshape(xx.shape).contiguous().to(x.dtype)
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, *, out=None):
+    return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(x.dtype)
+
+
+def attention(q, k, v, heads, *, scale=None, mask=None, out=None, impl=0):
+    B, Nq, C = q.shape
+    d = C // heads
+    scale = d ** -0.5 if scale is None else scale
+    qh = q.float().reshape(B, Nq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().reshape(B, -1, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if mask is not None:
+        s = s.masked_fill(~mask.bool()[:, None, None, :], -torch.finfo(s.dtype).max)
+    o = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+    return o.to(q.dtype)
+
+
+def audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode, *, out=None):
+    ap = F.linear(F.gelu(F.linear(audio.float(), w1.float(), b1)), w2.float(), b2)
+    if mode == real_ops.AUDIO_ADD:
+        return (ehs.float() + torch.sigmoid(alpha) * ap.mean(dim=1, keepdim=True)).to(ehs.dtype)
+    if ap.shape[1] > 4:
+        ap = F.adaptive_avg_pool1d(ap.transpose(1, 2), 4).transpose(1, 2)
+    return torch.cat([ehs.float(), ap], dim=1).to(ehs.dtype)
+
+
+def timestep_embedding(t, dim=320, *, out=None):
+    half = dim // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    a = t.float()[:, None] * f[None]
+    return torch.cat([torch.cos(a), torch.sin(a)], -1)
+
+
+def unary(x, act=0, *, out_dtype=None, out=None):
+    return ACT[act](x.float()).to(out_dtype or x.dtype)
+
+
+def cast(x, dtype, *, out=None):
+    return x.to(dtype)
+
+
+def add(a, b, *, out=None):
+    return a + b
+
+
+def upsample2x(x, *, out=None):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+
+
+def concat(x1, x2, *, out=None):
+    return torch.cat([x1, x2], dim=-1)
+
+
+def nchw_to_nhwc(x, dtype, *, out=None):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nhwc_to_nchw(x, *, out=None):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def cfg_sched_step(eps2, x, xin2, guidance, coef, trace=None):
+    B = x.shape[0]
+    e = eps2.float().permute(0, 3, 1, 2) if eps2.dim() == 4 else eps2.float().reshape(2 * B, x.shape[2], x.shape[3], 4).permute(0, 3, 1, 2)
+    eu, ec = e[:B], e[B:]
+    x.copy_(coef[0] * x + coef[1] * (eu + guidance * (ec - eu)))
+    if trace is not None:
+        trace.copy_(x)
+    xi = (x * coef[2]).permute(0, 2, 3, 1).to(xin2.dtype)
+    xin2.copy_(torch.cat([xi, xi], 0).reshape(xin2.shape))
+    return x
+
+
+def softmax_rows(x, scale=1.0, *, out=None):
+    return torch.softmax(x.float() * scale, -1).to(x.dtype)
+
+
+def transpose(x, *, out=None):
+    return x.transpose(1, 2).contiguous()
+
+
+def bcast_add(a, b, B, K, D, a_mode, b_mode, *, out=None):
+    def view(t, m):
+        return t.reshape(B, K, D) if m == 0 else (t.reshape(B, 1, D) if m == 1 else t.reshape(1, K, D))
+    return (view(a, a_mode) + view(b, b_mode)).expand(B, K, D).contiguous()
+
+
+def hier_assign(tokens, anchors, w1, b1, w2, b2, temperature):
+    t = tokens.float()
+    sim = torch.einsum("bkd,ld->bkl", F.normalize(t, dim=-1), F.normalize(anchors.float(), dim=-1)) * 10.0
+    gate = F.linear(F.gelu(F.linear(t, w1.float(), b1)), w2.float(), b2)
+    return torch.softmax((sim + gate) / temperature, dim=-1)
+
+
+def hier_route(tok10, assign, hw, routing, gates):
+    a = assign
+    if hw is not None:
+        a = a * hw[:, None, :]
+        a = a / (a.sum(-1, keepdim=True) + 1e-8)
+    r = a @ torch.softmax(routing, dim=1)
+    return tuple((tok10.float() * r[:, :, i:i + 1] * torch.sigmoid(gates[i])).to(tok10.dtype) for i in range(3))
+
+
+def norm_scale(x, target=60.0, per_sample=False, *, out=None):
+    n = x.float().norm(dim=-1, keepdim=True)
+    m = n.mean(dim=(1, 2), keepdim=True) if per_sample else n.mean()
+    return (x.float() * torch.where(m > 0, target / m, torch.ones_like(m))).to(x.dtype)
+
+
+def legacy_combine(fg, bg, amb, hierarchy_weights, D):
+    B = fg.shape[0]
+    w = torch.softmax(hierarchy_weights, 0)
+    return torch.cat([fg.reshape(B, -1, D) * w[0], bg.reshape(B, -1, D) * w[1], amb.reshape(B, -1, D) * w[2]], 1)
+
+
+_NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and hasattr(real_ops, n)
+          and n not in ("installed",)]
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap every libc2d-backed op for its torch double (and lift the CUDA-only guards)."""
+    saved = {n: getattr(real_ops, n) for n in _NAMES}
+    try:
+        for n in _NAMES:
+            setattr(real_ops, n, globals()[n])
+        real_ops.TEST_DOUBLE = True
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(real_ops, n, f)
+        real_ops.TEST_DOUBLE = False
