@@ -286,7 +286,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool linear_tc_supported(const void* x, const void* w, int M, int N, int K, int ldx) {
-  return M >= 1 && N >= 8 && K >= 8 && K % 8 == 0 && ldx % 8 == 0 && al16(x) && al16(w);
+  return M >= 1 && N >= 1 && K >= 8 && K % 8 == 0 && ldx % 8 == 0 && al16(x) && al16(w);
 }
 
 int linear_tc(const void* x, const void* w, const float* bias, const float* rowvec, int rows_per_vec,
@@ -324,7 +324,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int Cin, int Cout, int stride, int up) {
-  return stride == 1 && !up && Cin % 8 == 0 && Cin >= 64 && Cout >= 8 && is_pow2(W) && is_pow2(H) && al16(x) && al16(w) &&
+  return stride == 1 && !up && Cin % 8 == 0 && Cin >= 64 && Cout >= 1 && is_pow2(W) && is_pow2(H) && al16(x) && al16(w) &&
          ((long long)H * W >= 128 || 128 % (H * W) == 0);
 }
 

@@ -60,13 +60,19 @@ def _rows(x: torch.Tensor):
     M = 1
     for s in x.shape[:-1]:
         M *= s
-    ld = x.stride(-2)
-    # leading dims must be collapsible onto the row stride
-    exp = ld
+    # row stride = stride of the innermost leading dim with extent > 1 (extent-1 dims may carry any stride,
+    # e.g. numpy's 0 for a[None]); the remaining leading dims must collapse onto it
+    ld, exp = K, None
     for dim in range(x.dim() - 2, -1, -1):
-        if x.shape[dim] != 1 and x.stride(dim) != exp:
-            raise ValueError(f"tensor with shape {tuple(x.shape)} strides {x.stride()} is not a strided row matrix")
-        exp *= x.shape[dim]
+        if x.shape[dim] == 1:
+            continue
+        if exp is None:
+            ld = x.stride(dim)
+            exp = ld * x.shape[dim]
+        else:
+            if x.stride(dim) != exp:
+                raise ValueError(f"tensor with shape {tuple(x.shape)} strides {x.stride()} is not a strided row matrix")
+            exp *= x.shape[dim]
     return M, K, ld
 
 

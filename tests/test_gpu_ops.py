@@ -206,7 +206,8 @@ def test_audio_context(dtype, mode, K):
 
 def test_elementwise_and_layout():
     t = torch.tensor([981.0, 1.0, 500.0], device=DEV)
-    assert rel(ops.timestep_embedding(t, 320), T.timestep_embedding(t, 320)) < 2e-6
+    # angles reach ~1e3 rad: a 1-ulp difference in the fp32 frequency moves cos/sin by ~6e-5
+    assert rel(ops.timestep_embedding(t, 320), T.timestep_embedding(t, 320)) < 2e-5
     x = rnd(3, 1000, 640)
     assert rel(ops.geglu(x), T.geglu(x)) < 1e-6
     assert rel(ops.unary(x, ops.ACT_SILU), T.unary(x, 2)) < 1e-6

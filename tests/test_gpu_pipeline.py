@@ -96,18 +96,23 @@ def test_config2_first_steps_and_graph_equals_eager(gold, W, pipe32, pipe16):
         assert np.array_equal(oute["trace"][i], out16["trace"][i]), i
 
 
-def test_batch_invariance_and_euler(W, pipe16):
+def test_batch_invariance_and_euler(W, pipe32, pipe16):
     """Data-parallel invariance: an image's latents do not depend on what else is in its micro-batch."""
     seeds, prompts = [3, 4, 5], ["a beach", "a city", "a forest"]
     clap = np.stack([PL.clap_embedding(s) for s in seeds])
     cc = np.stack([PL.text_states(p) for p in prompts])
     cu = np.stack([PL.text_states("")] * 3)
     nz = np.stack([PL.init_noise(s) for s in seeds])
-    full = pipe16.generate(clap, cc, cu, nz, steps=50, decode=False, max_steps=3)["latents"]
-    for i in range(3):
-        one = pipe16.generate(clap[i:i + 1], cc[i:i + 1], cu[i:i + 1], nz[i:i + 1], steps=50, decode=False, max_steps=3)["latents"]
-        assert rel_l2(_t(one), _t(full[i:i + 1])) < 2e-3, i
+    # fp32 kernels: identical up to summation order; bf16: rounding flips are amplified like any bf16 error
+    for pipe, tol, nsteps in ((pipe32, 1e-5, 2), (pipe16, 1e-2, 3)):
+        full = pipe.generate(clap, cc, cu, nz, steps=50, decode=False, max_steps=nsteps)["latents"]
+        for i in range(3):
+            one = pipe.generate(clap[i:i + 1], cc[i:i + 1], cu[i:i + 1], nz[i:i + 1], steps=50, decode=False,
+                                max_steps=nsteps)["latents"]
+            assert rel_l2(_t(one), _t(full[i:i + 1])) < tol, (pipe.dtype, i)
     # Euler scheduler against the oracle (fp32 oracle on the GPU as the checker)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     Wg = {k: {n: t.to(DEV) for n, t in v.items()} for k, v in W.items() if k != "vae" and k != "adapter"}
     ref = PL.sample(Wg, _t(clap[:1]).to(DEV), _t(cc[:1]).to(DEV), _t(cu[:1]).to(DEV), _t(nz[:1]).to(DEV), steps=50,
                     scheduler="euler", max_steps=2)
