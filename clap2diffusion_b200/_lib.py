@@ -39,6 +39,7 @@ SIGNATURES = {
     "c2d_last_error": [],
     "c2d_init": [_i],
     "c2d_launch_count": [],
+    "c2d_last_kernel": [],
     "c2d_linear": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "c2d_geglu_linear": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "c2d_conv3x3": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -65,7 +66,7 @@ SIGNATURES = {
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }
-_RESTYPES = {"c2d_last_error": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
+_RESTYPES = {"c2d_last_error": C.c_char_p, "c2d_last_kernel": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = symbol missing from the .so

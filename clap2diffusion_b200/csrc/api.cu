@@ -39,7 +39,7 @@ int c2d_linear(const void* x, const void* w, const float* bias, const float* row
     C2D_REQUIRE(tc_ok, "linear: tcgen05 path needs bf16, K %% 8 == 0, ldx %% 8 == 0, aligned pointers");
     return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
   }
-  if (impl == C2D_IMPL_AUTO && tc_ok && M >= 64 && N >= 32)
+  if (impl == C2D_IMPL_AUTO && tc_ok && M >= 64)
     return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
   return linear_simt(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, dtype, s);
 }
@@ -67,7 +67,7 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
     C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, stride 1, no fused upsample, pow2 H/W, Cin %% 8 == 0, Cin >= 64");
     return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
   }
-  if (impl == C2D_IMPL_AUTO && tc_ok && Cout >= 32)
+  if (impl == C2D_IMPL_AUTO && tc_ok)
     return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
   return conv3x3_simt(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, upsample2x, dtype, s);
 }

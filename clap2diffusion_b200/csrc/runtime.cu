@@ -7,6 +7,7 @@
 namespace c2d {
 
 static thread_local char g_err[512] = "";
+static thread_local const char* g_last_kernel = "";
 std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -18,6 +19,7 @@ void set_error(const char* fmt, ...) {
 
 int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_kernel = what;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -38,6 +40,8 @@ int c2d_abi_version(void) { return C2D_ABI_VERSION; }
 const char* c2d_last_error(void) { return c2d::g_err; }
 
 unsigned long long c2d_launch_count(void) { return c2d::g_launches.load(); }
+
+const char* c2d_last_kernel(void) { return c2d::g_last_kernel; }
 
 int c2d_init(int device) {
   int n = 0;

@@ -20,6 +20,35 @@ AUDIO_ADD, AUDIO_CONCAT = _lib.AUDIO_ADD, _lib.AUDIO_CONCAT
 # machine without a GPU).  The product never sets it; with it False every op demands CUDA tensors.
 TEST_DOUBLE = False
 
+# Per-op profiling for bench.py's roofline: when PROFILE is a list, every op appends
+# (kernel_name, flops, bytes, start_event, end_event) recorded on the launching stream.
+PROFILE = None
+
+
+class _Timed:
+    __slots__ = ("flops", "nbytes", "e0")
+
+    def __init__(self, flops=0.0, nbytes=0.0):
+        self.flops, self.nbytes = flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append(((lib.c2d_last_kernel() or b"?").decode(), float(self.flops), float(self.nbytes), self.e0, e1))
+        return False
+
+
+def _nb(*tensors) -> float:
+    return float(sum(t.numel() * t.element_size() for t in tensors if t is not None))
+
+
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
 
@@ -92,9 +121,10 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_pe
     if residual is not None:
         Mr, Nr, ldr = _rows(residual)
         assert Mr == M and Nr == N and residual.dtype == x.dtype
-    check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
-                         int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
-                         impl, _stream()), "linear")
+    with _Timed(2.0 * M * N * K, _nb(w, residual) + (M * K + M * N) * x.element_size()):
+        check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                             int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
+                             impl, _stream()), "linear")
     return out
 
 
@@ -106,8 +136,9 @@ def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=IMPL_AUTO):
     F = w_packed.shape[0] // 2
     if out is None:
         out = torch.empty(*x.shape[:-1], F, device=x.device, dtype=x.dtype)
-    check(lib.c2d_geglu_linear(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")), out.data_ptr(),
-                               M, F, K, 1, _dt(x), impl, _stream()), "geglu_linear")
+    with _Timed(4.0 * M * F * K, _nb(x, w_packed, out)):
+        check(lib.c2d_geglu_linear(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")), out.data_ptr(),
+                                   M, F, K, 1, _dt(x), impl, _stream()), "geglu_linear")
     return out
 
 
@@ -125,9 +156,10 @@ def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, ups
     assert out.is_contiguous() and out.numel() == B * Ho * Wo * Cout
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == out.numel() and residual.dtype == x.dtype
-    check(lib.c2d_conv3x3(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
-                          _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout, stride, int(bool(upsample)), _dt(x),
-                          impl, _stream()), "conv3x3")
+    with _Timed(2.0 * B * Ho * Wo * Cout * 9 * Cin, _nb(x, w_packed, out, residual)):
+        check(lib.c2d_conv3x3(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                              _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout, stride, int(bool(upsample)), _dt(x),
+                              impl, _stream()), "conv3x3")
     return out
 
 
@@ -152,9 +184,10 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_
     if out is None:
         out = torch.empty(*x.shape[:-1], C1 + C2, device=x.device, dtype=x.dtype)
     ws = _gn_workspace(x.device, B * groups * 2)
-    check(lib.c2d_group_norm(x.data_ptr(), _ptr(x2), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
-                             out.data_ptr(), _ptr(raw_cat), ws.data_ptr(), B, N, C1, C2, groups, float(eps),
-                             int(bool(silu)), _dt(x), _stream()), "group_norm")
+    with _Timed(0.0, 2 * _nb(x, x2) + _nb(out, raw_cat)):     # stats pass + apply pass read the input twice
+        check(lib.c2d_group_norm(x.data_ptr(), _ptr(x2), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                                 out.data_ptr(), _ptr(raw_cat), ws.data_ptr(), B, N, C1, C2, groups, float(eps),
+                                 int(bool(silu)), _dt(x), _stream()), "group_norm")
     return out
 
 
@@ -165,8 +198,9 @@ def layer_norm(x, gamma, beta, eps=1e-5, *, out=None):
     M = x.numel() // C
     if out is None:
         out = torch.empty_like(x)
-    check(lib.c2d_layer_norm(x.data_ptr(), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
-                             out.data_ptr(), M, C, float(eps), _dt(x), _stream()), "layer_norm")
+    with _Timed(0.0, _nb(x, out)):
+        check(lib.c2d_layer_norm(x.data_ptr(), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                                 out.data_ptr(), M, C, float(eps), _dt(x), _stream()), "layer_norm")
     return out
 
 
@@ -186,10 +220,11 @@ def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, 
         scale = d ** -0.5
     if mask is not None:
         assert mask.dtype in (torch.bool, torch.uint8) and mask.is_contiguous() and tuple(mask.shape) == (B, Nkv)
-    check(lib.c2d_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nkv, d,
-                            q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0),
-                            v.stride(0), out.stride(0), float(scale), _ptr(mask), _dt(q), impl, _stream()),
-          "attention")
+    with _Timed(4.0 * B * heads * Nq * Nkv * d, (2 * B * Nq * C + 2 * B * Nkv * C) * q.element_size()):
+        check(lib.c2d_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nkv, d,
+                                q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0),
+                                v.stride(0), out.stride(0), float(scale), _ptr(mask), _dt(q), impl, _stream()),
+              "attention")
     return out
 
 
@@ -261,7 +296,8 @@ def upsample2x(x, *, out=None):
     assert x.is_contiguous()
     if out is None:
         out = torch.empty(B, 2 * H, 2 * W, Cc, device=x.device, dtype=x.dtype)
-    check(lib.c2d_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _dt(x), _stream()), "upsample2x")
+    with _Timed(0.0, _nb(x, out)):
+        check(lib.c2d_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, Cc, _dt(x), _stream()), "upsample2x")
     return out
 
 

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .schedulers import make_plan
 from .unet import SD15UNet
 from .vae import VAEDecoder
@@ -24,6 +24,7 @@ class Sampler:
         self.unet, self.hier, self.vae = unet, hier, vae
         self.use_graph = use_graph
         self._graphs: Dict[tuple, dict] = {}
+        self.replayed_launches = 0      # kernels launched through graph replays (not seen by c2d_launch_count)
 
     # ------------------------------------------------------------------ conditioning (once per batch)
     @torch.no_grad()
@@ -89,6 +90,7 @@ class Sampler:
                 if st["graph"] is None:
                     st["graph"] = self._capture(st)
                 st["graph"].replay()
+                self.replayed_launches += st["launches_per_replay"]
             else:
                 self._step(st)
             if trace:
@@ -112,8 +114,10 @@ class Sampler:
         st["x"].copy_(x0)
         st["xin2"].copy_(xin0)
         g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(g):
             self._step(st)
+        st["launches_per_replay"] = _lib.launch_count() - n0     # kernels one replay launches
         st["x"].copy_(x0)          # capture does not execute; keep the state untouched anyway
         st["xin2"].copy_(xin0)
         return g

@@ -42,6 +42,9 @@ const char* c2d_last_error(void);
 int c2d_init(int device);
 /* Number of kernels this library has launched since load (claim for bench.py's gpu_launches). */
 unsigned long long c2d_launch_count(void);
+/* Name of the kernel family the calling thread launched last (e.g. "conv3x3_tc", "linear_simt"): lets
+ * the benchmark attribute CUDA-event timings to the kernel C2D_IMPL_AUTO actually picked. */
+const char* c2d_last_kernel(void);
 
 /* ---- dense layer:  y[M,N] = act(x[M,K] . w[N,K]^T + bias[N] + rowvec[m / rows_per_vec][N]) + residual[M,N]
  * Replaces nn.Linear / 1x1 conv calls: attn.to_q/to_k/to_v/to_out[0]

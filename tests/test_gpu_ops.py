@@ -172,6 +172,29 @@ def test_attention_simt(B, h, Nq, Nkv, d, dtype):
     assert rel(o, T.attention(q, k, v, h)) < (2e-5 if dtype == F32 else 1e-2)
 
 
+ATT_TC = [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
+          (2, 8, 4096, 77, 40), (2, 8, 1024, 81, 80), (1, 8, 256, 77, 160), (2, 4, 200, 333, 64), (1, 2, 130, 129, 16)]
+
+
+@pytest.mark.parametrize("B,h,Nq,Nkv,d", ATT_TC)
+def test_attention_tcgen05(B, h, Nq, Nkv, d):
+    C = h * d
+    if Nq == Nkv:        # self-attention: views of one packed QKV buffer, as the UNet uses it
+        qkv = rnd(B, Nq, 3 * C, dtype=BF16)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:                # cross-attention: q dense, K/V views of the cached [B, T, 2C] buffer
+        q = rnd(B, Nq, C, dtype=BF16)
+        kv = rnd(B, Nkv, 2 * C, dtype=BF16, seed=1)
+        k, v = kv[..., :C], kv[..., C:]
+    o = ops.attention(q, k, v, h, impl=ops.IMPL_TCGEN05)
+    ref = T.attention(q, k, v, h)
+    assert rel(o, ref) < 1e-2
+    assert rel(o, ops.attention(q, k, v, h, impl=ops.IMPL_SIMT)) < 1e-2
+    # large-magnitude logits exercise the lazy-rescale path
+    o2 = ops.attention(q * 6, k, v, h, impl=ops.IMPL_TCGEN05)
+    assert rel(o2, T.attention(q * 6, k, v, h)) < 2e-2
+
+
 def test_attention_packed_views_mask_and_small():
     B, N_, C, h = 2, 256, 320, 8
     qkv = rnd(B, N_, 3 * C)
