@@ -160,7 +160,31 @@ def per_kernel_profile(pipe, m: int):
     return agg
 
 
+def run_ncu_step(args):
+    """`--ncu-step`: one eager UNet denoising step at the benchmark batch between cudaProfilerStart/Stop, for
+    `ncu --profile-from-start off` (launch list / --set full captures under profiles/)."""
+    import contextlib
+    from clap2diffusion_b200.pipeline import AudioToImagePipeline
+    dev = torch.device("cuda", 0)
+    with contextlib.redirect_stdout(sys.stderr):
+        pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16, with_vae=False)
+    m = args.micro_batch
+    x = torch.randn(2 * m, LATENT, LATENT, 4, device=dev).to(torch.bfloat16)
+    ctx = torch.randn(2 * m, 77, 768, device=dev).to(torch.bfloat16)
+    kv = pipe.unet.prepare_conditioning(ctx, None)
+    table = pipe.unet.time_table([500.0])
+    for _ in range(2):
+        pipe.unet.forward_nhwc(x, table[0], kv)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    pipe.unet.forward_nhwc(x, table[0], kv)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print(json.dumps({"ncu_step": "done", "micro_batch": m}))
+
+
 def run_ours(args):
+    import contextlib
     import torch.distributed as dist
     from clap2diffusion_b200 import _lib, synthetic
     from clap2diffusion_b200.pipeline import AudioToImagePipeline, gather_latents
@@ -175,7 +199,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     m = args.micro_batch
-    pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16)
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
+        pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16)
 
     def job_inputs(step: int):
         # (prompt, seed) jobs: 8 prompts x seeds, unique per (rank, step, slot)
@@ -310,8 +335,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--ncu-step", action="store_true", help="profile one eager UNet step (for ncu --profile-from-start off)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.ncu_step:
+        run_ncu_step(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -12,7 +12,7 @@ bool linear_tc_supported(const void*, const void*, int, int, int, int);
 int linear_tc(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int, int,
               int, bool, cudaStream_t);
 bool conv3x3_tc_supported(const void*, const void*, int, int, int, int, int, int, int);
-int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int,
+int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int,
                cudaStream_t);
 int attention_simt(const AttnParams&, int, int, cudaStream_t);
 int attention_small(const AttnParams&, int, int, cudaStream_t);
@@ -64,11 +64,11 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, upsample2x);
   if (impl == C2D_IMPL_TCGEN05) {
-    C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, stride 1, no fused upsample, pow2 H/W, Cin %% 8 == 0, Cin >= 64");
-    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
+    C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, no fused upsample, pow2 output H/W, Cin %% 8 == 0, Cin >= 64");
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, s);
   }
   if (impl == C2D_IMPL_AUTO && tc_ok)
-    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, s);
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, s);
   return conv3x3_simt(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, upsample2x, dtype, s);
 }
 

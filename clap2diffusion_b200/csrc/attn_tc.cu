@@ -164,72 +164,96 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int kvalid = min(AT_BK, p.Nkv - j * AT_BK);
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      // ---- pass 1: row max (in the scaled log2 domain)
-      float mx = -INFINITY;
+      if (j == 0) {
+        // first tile: the reference max must be known before any exponential is taken
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
-        tmem_ld_wait();
-        if (c * 32 < kvalid) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(r[i]);
-            if (c * 32 + i < kvalid) mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        m_ref = mx * p.scale_log2;
+      } else {
+        mbar_wait(p_empty, (uint32_t)(j - 1) & 1u);     // PV(j-1) retired: P smem free, O complete
+      }
+      // ---- single pass in the common case: p = exp2(s * scale_log2 - m_ref) against the LAGGING reference max,
+      //      tracking the tile max on the side.  Only if some row's max moved by more than 2^8 is the tile redone
+      //      with the new reference and the O accumulator rescaled (rare after the first tiles).
+      float sum, mx;
+      float alpha = 1.f;
+      bool redo = false;
+      for (;;) {
+        sum = 0.f;
+        mx = -INFINITY;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tmem_s + lane_off, ra);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&r)[32] = (c & 1) ? rb : ra;
+          uint32_t (&rn)[32] = (c & 1) ? ra : rb;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(tmem_s + lane_off + (c + 1) * 32, rn);    // prefetch next chunk
+          uint32_t packed[16];
+          if (kvalid == AT_BK) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+              mx = fmaxf(mx, fmaxf(s0, s1));
+              __nv_bfloat162 hb = __floats2bfloat162_rn(ex2f(fmaf(s0, p.scale_log2, -m_ref)), ex2f(fmaf(s1, p.scale_log2, -m_ref)));
+              sum += __low2float(hb) + __high2float(hb);      // what the tensor core will actually see
+              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const bool v0 = c * 32 + i < kvalid, v1 = c * 32 + i + 1 < kvalid;
+              const float s0 = v0 ? __uint_as_float(r[i]) : -INFINITY, s1 = v1 ? __uint_as_float(r[i + 1]) : -INFINITY;
+              mx = fmaxf(mx, fmaxf(s0, s1));
+              __nv_bfloat162 hb = __floats2bfloat162_rn(v0 ? ex2f(fmaf(s0, p.scale_log2, -m_ref)) : 0.f,
+                                                        v1 ? ex2f(fmaf(s1, p.scale_log2, -m_ref)) : 0.f);
+              sum += __low2float(hb) + __high2float(hb);
+              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+            }
+          }
+          // 32 keys = 4 chunks of 16 B; key block (64 keys) = c >> 1, chunk index within the 128 B row = (c & 1) * 4 + q
+          uint8_t* blk = p_row + (c >> 1) * AT_TILE;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ rsw;
+            *reinterpret_cast<uint4*>(blk + (chunk << 4)) =
+                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
           }
         }
+        if (redo) break;
+        mx *= p.scale_log2;
+        const bool need = mx > m_ref + 8.0f;
+        if (!__any_sync(0xffffffffu, need)) break;
+        if (need) {
+          alpha = ex2f(m_ref - mx);
+          m_ref = mx;
+        }
+        redo = true;
       }
-      mx *= p.scale_log2;
-      // ---- lazy rescale decision (warp-collective TMEM traffic only when some row's max moved by > 2^8)
-      const bool need = mx > m_ref + 8.0f;
-      float alpha = 1.f;
-      if (need) {
-        alpha = ex2f(m_ref - mx);       // j == 0: exp2(-inf) = 0
-        m_ref = mx;
-      }
-      const bool warp_need = __any_sync(0xffffffffu, need) && j > 0;
-      if (j > 0) mbar_wait(p_empty, (uint32_t)(j - 1) & 1u);     // PV(j-1) retired: P smem free, O complete
-      if (warp_need) {
-        tc_fence_after();
+      if (redo && j > 0) {
+        // warp-collective rescale of the O accumulator (rows that did not move use alpha = 1)
         for (int c = 0; c < p.npv; c += 16) {
           uint32_t r[16];
           tmem_ld_32x16(tmem_o + lane_off + c, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
           uint32_t lo[8], hi[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { lo[i] = r[i]; hi[i] = r[8 + i]; }
+          for (int i = 0; i < 8; ++i) {
+            lo[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            hi[i] = __float_as_uint(__uint_as_float(r[8 + i]) * alpha);
+          }
           tmem_st_32x8(tmem_o + lane_off + c, lo);
           tmem_st_32x8(tmem_o + lane_off + c + 8, hi);
         }
         tmem_st_wait();
-      }
-      // ---- pass 2: p = exp2(s * scale_log2 - m_ref), row sum, bf16 P into the swizzled K-major smem tile
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
-        tmem_ld_wait();
-        uint32_t packed[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kvalid) ? ex2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref)) : 0.f;
-          float p1 = (c * 32 + i + 1 < kvalid) ? ex2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref)) : 0.f;
-          __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          // sum what the tensor core will actually see (bf16-rounded probabilities)
-          sum += __low2float(hb) + __high2float(hb);
-          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-        }
-        // 32 keys = 4 chunks of 16 B; key block (64 keys) = c >> 1, chunk index within the 128 B row = (c & 1) * 4 + q
-        uint8_t* blk = p_row + (c >> 1) * AT_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ rsw;
-          *reinterpret_cast<uint4*>(blk + (chunk << 4)) =
-              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-        }
       }
       l_run = l_run * alpha + sum;
       tc_fence_before();

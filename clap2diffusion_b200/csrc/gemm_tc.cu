@@ -33,8 +33,8 @@ struct TcParams {
   int rows_per_vec;
   int act;
   int num_k_blocks;
-  // conv geometry
-  int HW, W, Cin, cblocks;
+  // conv geometry (HW, W: OUTPUT plane; cstride: convolution stride 1 | 2)
+  int HW, W, Cin, cblocks, cstride;
 };
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -54,13 +54,13 @@ static int get_encode() {
 }
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost-first; strides in BYTES for dims 1..rank-1.
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+int make_tmap_bf16_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   int rc = get_encode();
   if (rc) return rc;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -74,6 +74,11 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
     return C2D_ERR_CUDA;
   }
   return C2D_OK;
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return make_tmap_bf16_strided(m, base, rank, dims, strides_bytes, box, nullptr);
 }
 
 template <int BN>
@@ -150,7 +155,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.cblocks;
           const int c0 = (kb - tap * p.cblocks) * TC_BK;
           const int ky = tap / 3, kx = tap - ky * 3;
-          tma_load_4d(sA, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b0);
+          // stride-2: the tensor map traverses the input with element strides {1,2,2,1}
+          tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
           tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
         } else {
           tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
@@ -324,24 +330,30 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int Cin, int Cout, int stride, int up) {
-  return stride == 1 && !up && Cin % 8 == 0 && Cin >= 64 && Cout >= 1 && is_pow2(W) && is_pow2(H) && al16(x) && al16(w) &&
-         ((long long)H * W >= 128 || 128 % (H * W) == 0);
+  if (up || (stride != 1 && stride != 2)) return false;
+  if (stride == 2 && ((H & 1) || (W & 1))) return false;
+  const int Ho = H / stride, Wo = W / stride;
+  return Cin % 8 == 0 && Cin >= 64 && Cout >= 1 && is_pow2(Wo) && is_pow2(Ho) && al16(x) && al16(w) &&
+         ((long long)Ho * Wo >= 128 || 128 % (Ho * Wo) == 0) && (stride == 1 || Wo <= 128);
 }
 
 int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
-               int H, int W, int Cin, int Cout, cudaStream_t s) {
-  C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, 1, 0),
-              "conv3x3_tc: needs stride 1, pow2 H/W, Cin %% 8 == 0, Cin >= 64 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
-  const int bw = W < 128 ? W : 128;
-  const int bh = (128 / bw) < H ? (128 / bw) : H;
+               int H, int W, int Cin, int Cout, int stride, cudaStream_t s) {
+  C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
+              "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0, Cin >= 64 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+  const int Ho = H / stride, Wo = W / stride;
+  const int bw = Wo < 128 ? Wo : 128;
+  const int bh = (128 / bw) < Ho ? (128 / bw) : Ho;
   const int bb = 128 / (bw * bh);
   const int BN = (Cout % 160 == 0) ? 160 : 128;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t st[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
-    uint32_t box[4] = {TC_BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
-    int rc = make_tmap_bf16(&tmA, x, 4, dims, st, box);
+    // box extents are in traversed input elements: with element stride 2 a box of 2*bw loads bw pixels
+    uint32_t box[4] = {TC_BK, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bb};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = make_tmap_bf16_strided(&tmA, x, 4, dims, st, box, es);
     if (rc) return rc;
   }
   {
@@ -353,10 +365,10 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   }
   TcParams p = {};
   p.bias = bias; p.rowvec = rowvec; p.residual = reinterpret_cast<const bf16*>(residual); p.y = reinterpret_cast<bf16*>(y);
-  p.M = B * H * W; p.N = Cout; p.K = 9 * Cin; p.ldy = Cout; p.ldr = Cout;
-  p.rows_per_vec = H * W;
+  p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin; p.ldy = Cout; p.ldr = Cout;
+  p.rows_per_vec = Ho * Wo;
   p.act = C2D_ACT_NONE;
-  p.HW = H * W; p.W = W; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK);
+  p.HW = Ho * Wo; p.W = Wo; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK); p.cstride = stride;
   p.num_k_blocks = 9 * p.cblocks;
   if (BN == 160) return launch_tc<160, true, false>(tmA, tmB, p, s);
   return launch_tc<128, true, false>(tmA, tmB, p, s);

@@ -8,6 +8,7 @@ namespace c2d {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_ITERS = 2;        // C <= 8 * 256 * 2 = 4096
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_UNROLL = 4;
 
 template <typename T>
 __device__ __forceinline__ void gn_load(const T* __restrict__ x, const T* __restrict__ x2, long long row, int c,
@@ -21,14 +22,11 @@ template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __restrict__ stats, int HW, int C1, int C2,
                 int groups, int rows_per_cta) {
-  __shared__ double s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
   const int C = C1 + C2, nvec = C >> 3, cpg = C / groups;
   const int nvec_eff = nvec < GN_THREADS ? nvec : GN_THREADS;
   const int rows_in_flight = GN_THREADS / nvec_eff;
   const int my_vec = threadIdx.x % nvec_eff, my_rl = threadIdx.x / nvec_eff;
   const int b = blockIdx.y;
-  if (threadIdx.x < groups) { s_sum[threadIdx.x] = 0.0; s_sq[threadIdx.x] = 0.0; }
-  __syncthreads();
   float acc[GN_MAX_ITERS][8], acq[GN_MAX_ITERS][8];
 #pragma unroll
   for (int it = 0; it < GN_MAX_ITERS; ++it)
@@ -37,36 +35,59 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
   if (my_rl < rows_in_flight) {
-    for (int r = r0 + my_rl; r < r1; r += rows_in_flight) {
-      long long row = (long long)b * HW + r;
+    // GN_UNROLL independent 128-bit loads in flight per thread (memory-level parallelism)
+    for (int r = r0 + my_rl; r < r1; r += GN_UNROLL * rows_in_flight) {
+      float f[GN_UNROLL][GN_MAX_ITERS][8];
 #pragma unroll
-      for (int it = 0; it < GN_MAX_ITERS; ++it) {
-        int vec = my_vec + it * nvec_eff;
-        if (vec < nvec) {
-          float f[8];
-          gn_load<T>(x, x2, row, vec * 8, C1, C2, f);
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int rr = r + u * rows_in_flight;
+        const long long row = (long long)b * HW + rr;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { acc[it][j] += f[j]; acq[it][j] += f[j] * f[j]; }
+        for (int it = 0; it < GN_MAX_ITERS; ++it) {
+          const int vec = my_vec + it * nvec_eff;
+          if (rr < r1 && vec < nvec) gn_load<T>(x, x2, row, vec * 8, C1, C2, f[u][it]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[u][it][j] = 0.f;
+          }
         }
       }
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u)
+#pragma unroll
+        for (int it = 0; it < GN_MAX_ITERS; ++it)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[it][j] += f[u][it][j]; acq[it][j] += f[u][it][j] * f[u][it][j]; }
     }
+  }
+  // per-(row lane, channel) fp32 partials -> smem, then one thread per group folds them in double
+  // (rows_in_flight * C == 8 * GN_THREADS floats per array whenever C <= 8 * GN_THREADS)
+  extern __shared__ float s_part[];
+  float* s_ps = s_part;
+  float* s_pq = s_part + rows_in_flight * C;
+  if (my_rl < rows_in_flight) {
 #pragma unroll
     for (int it = 0; it < GN_MAX_ITERS; ++it) {
-      int vec = my_vec + it * nvec_eff;
+      const int vec = my_vec + it * nvec_eff;
       if (vec < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          int g = (vec * 8 + j) / cpg;
-          atomicAdd(&s_sum[g], (double)acc[it][j]);
-          atomicAdd(&s_sq[g], (double)acq[it][j]);
+          s_ps[my_rl * C + vec * 8 + j] = acc[it][j];
+          s_pq[my_rl * C + vec * 8 + j] = acq[it][j];
         }
       }
     }
   }
   __syncthreads();
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    double a = 0.0, q = 0.0;
+    for (int rl = 0; rl < rows_in_flight; ++rl)
+      for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+        a += (double)s_ps[rl * C + c];
+        q += (double)s_pq[rl * C + c];
+      }
+    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 0], a);
+    atomicAdd(&stats[((long long)b * groups + threadIdx.x) * 2 + 1], q);
   }
 }
 
@@ -80,16 +101,21 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, const float* 
   float* s_a = sm;
   float* s_b = sm + C;
   const int b = blockIdx.y;
-  const double inv_n = 1.0 / ((double)HW * (double)cpg);
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    int g = c / cpg;
-    double mean = stats[((long long)b * groups + g) * 2 + 0] * inv_n;
-    double var = stats[((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean;
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  if (threadIdx.x < groups) {
+    const double inv_n = 1.0 / ((double)HW * (double)cpg);
+    double mean = stats[((long long)b * groups + threadIdx.x) * 2 + 0] * inv_n;
+    double var = stats[((long long)b * groups + threadIdx.x) * 2 + 1] * inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float a = rstd * gamma[c];
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * gamma[c];
     s_a[c] = a;
-    s_b[c] = beta[c] - (float)mean * a;
+    s_b[c] = beta[c] - s_mean[g] * a;
   }
   __syncthreads();
   const int nvec_eff = nvec < GN_THREADS ? nvec : GN_THREADS;
@@ -98,67 +124,93 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, const float* 
   if (my_rl >= rows_in_flight) return;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
-  for (int r = r0 + my_rl; r < r1; r += rows_in_flight) {
-    long long row = (long long)b * HW + r;
-    for (int vec = my_vec; vec < nvec; vec += nvec_eff) {
-      int c = vec * 8;
-      float f[8];
-      gn_load<T>(x, x2, row, c, C1, C2, f);
-      if (raw) Vec8<T>::store(raw + row * C + c, f);
+  for (int vec = my_vec; vec < nvec; vec += nvec_eff) {
+    const int c = vec * 8;
+    float a[8], sh[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = f[j] * s_a[c + j] + s_b[c + j];
-        f[j] = silu ? silu_acc(v) : v;
+    for (int j = 0; j < 8; ++j) { a[j] = s_a[c + j]; sh[j] = s_b[c + j]; }
+    for (int r = r0 + my_rl; r < r1; r += GN_UNROLL * rows_in_flight) {
+      float f[GN_UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int rr = r + u * rows_in_flight;
+        if (rr < r1) gn_load<T>(x, x2, (long long)b * HW + rr, c, C1, C2, f[u]);
       }
-      Vec8<T>::store(y + row * C + c, f);
+#pragma unroll
+      for (int u = 0; u < GN_UNROLL; ++u) {
+        const int rr = r + u * rows_in_flight;
+        if (rr < r1) {
+          const long long row = (long long)b * HW + rr;
+          if (raw) Vec8<T>::store(raw + row * C + c, f[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = f[u][j] * a[j] + sh[j];
+            f[u][j] = silu ? silu_acc(v) : v;
+          }
+          Vec8<T>::store(y + row * C + c, f[u]);
+        }
+      }
     }
   }
 }
 
-// ---- LayerNorm: one warp per row, row kept in registers when C % 8 == 0 and C <= 8*32*LN_MAXV ------
-constexpr int LN_MAXV = 5;   // 1280 channels
-
-template <typename T>
+// ---- LayerNorm: one warp handles ROWS rows at once (ROWS x ITERS independent 128-bit loads in flight per lane),
+// rows kept in registers, two-pass statistics in registers.  C % 8 == 0 and C <= 256 * ITERS.
+template <typename T, int ITERS, int ROWS>
 __global__ void ln_vec_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                               T* __restrict__ y, int M, int C, float eps) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int row0 = warp * ROWS;
+  if (row0 >= M) return;
   const int nvec = C >> 3;
-  const T* xr = x + (long long)warp * C;
-  float v[LN_MAXV][8];
-  float s = 0.f;
+  float v[ROWS][ITERS][8];
 #pragma unroll
-  for (int it = 0; it < LN_MAXV; ++it) {
-    int vec = lane + it * 32;
-    if (vec < nvec) {
-      Vec8<T>::load(xr + vec * 8, v[it]);
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[it][j];
-    }
-  }
-  float mean = warp_sum(s) / (float)C;
-  float q = 0.f;
+    for (int it = 0; it < ITERS; ++it) {
+      const int vec = lane + it * 32;
+      if (row0 + r < M && vec < nvec) Vec8<T>::load(x + (long long)(row0 + r) * C + vec * 8, v[r][it]);
+      else {
 #pragma unroll
-  for (int it = 0; it < LN_MAXV; ++it) {
-    int vec = lane + it * 32;
-    if (vec < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { float d = v[it][j] - mean; q += d * d; }
-    }
-  }
-  float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-  T* yr = y + (long long)warp * C;
-#pragma unroll
-  for (int it = 0; it < LN_MAXV; ++it) {
-    int vec = lane + it * 32;
-    if (vec < nvec) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int c = vec * 8 + j;
-        o[j] = (v[it][j] - mean) * rstd * gamma[c] + beta[c];
+        for (int j = 0; j < 8; ++j) v[r][it][j] = 0.f;
       }
-      Vec8<T>::store(yr + vec * 8, o);
+    }
+  float mean[ROWS], rstd[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[r][it][j];
+    mean[r] = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int vec = lane + it * 32;
+      if (vec < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float d = v[r][it][j] - mean[r]; q += d * d; }
+      }
+    }
+    rstd[r] = rsqrtf(warp_sum(q) / (float)C + eps);
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int vec = lane + it * 32;
+    if (vec < nvec) {
+      float g[8], bt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { g[j] = gamma[vec * 8 + j]; bt[j] = beta[vec * 8 + j]; }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r < M) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[r][it][j] - mean[r]) * rstd[r] * g[j] + bt[j];
+          Vec8<T>::store(y + (long long)(row0 + r) * C + vec * 8, o);
+        }
+      }
     }
   }
 }
@@ -206,14 +258,16 @@ int c2d_group_norm(const void* x, const void* x2, const float* gamma, const floa
   slabs = ceil_div(HW, rows_per_cta);
   dim3 grid(slabs, B);
   size_t smem = sizeof(float) * 2 * C;
+  const int nvec_eff_h = (C / 8) < GN_THREADS ? (C / 8) : GN_THREADS;
+  size_t smem_stats = sizeof(float) * 2 * (size_t)(GN_THREADS / nvec_eff_h) * C;
   if (dtype == C2D_F32) {
-    gn_stats_kernel<float><<<grid, GN_THREADS, 0, s>>>((const float*)x, (const float*)x2, stats_ws, HW, C1, C2, groups, rows_per_cta);
+    gn_stats_kernel<float><<<grid, GN_THREADS, smem_stats, s>>>((const float*)x, (const float*)x2, stats_ws, HW, C1, C2, groups, rows_per_cta);
     int rc = check_launch("gn_stats");
     if (rc) return rc;
     gn_apply_kernel<float><<<grid, GN_THREADS, smem, s>>>((const float*)x, (const float*)x2, gamma, beta, stats_ws,
                                                            (float*)y, (float*)raw_cat, HW, C1, C2, groups, eps, silu, rows_per_cta);
   } else if (dtype == C2D_BF16) {
-    gn_stats_kernel<bf16><<<grid, GN_THREADS, 0, s>>>((const bf16*)x, (const bf16*)x2, stats_ws, HW, C1, C2, groups, rows_per_cta);
+    gn_stats_kernel<bf16><<<grid, GN_THREADS, smem_stats, s>>>((const bf16*)x, (const bf16*)x2, stats_ws, HW, C1, C2, groups, rows_per_cta);
     int rc = check_launch("gn_stats");
     if (rc) return rc;
     gn_apply_kernel<bf16><<<grid, GN_THREADS, smem, s>>>((const bf16*)x, (const bf16*)x2, gamma, beta, stats_ws,
@@ -229,19 +283,19 @@ int c2d_layer_norm(const void* x, const float* gamma, const float* beta, void* y
                    void* stream) {
   C2D_REQUIRE(x && gamma && beta && y && M > 0 && C > 0, "layer_norm: bad args");
   cudaStream_t s = (cudaStream_t)stream;
-  int threads = 128, warps_per_cta = threads / 32;
-  int grid = ceil_div(M, warps_per_cta);
-  bool vec = (C % 8 == 0) && (C <= 8 * 32 * LN_MAXV);
-  if (dtype == C2D_F32) {
-    if (vec) ln_vec_kernel<float><<<grid, threads, 0, s>>>((const float*)x, gamma, beta, (float*)y, M, C, eps);
-    else ln_generic_kernel<float><<<grid, threads, 0, s>>>((const float*)x, gamma, beta, (float*)y, M, C, eps);
-  } else if (dtype == C2D_BF16) {
-    if (vec) ln_vec_kernel<bf16><<<grid, threads, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, M, C, eps);
-    else ln_generic_kernel<bf16><<<grid, threads, 0, s>>>((const bf16*)x, gamma, beta, (bf16*)y, M, C, eps);
-  } else {
-    set_error("layer_norm: bad dtype %d", dtype);
-    return C2D_ERR_ARG;
-  }
+  const int threads = 128, wpc = threads / 32;
+  C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "layer_norm: bad dtype %d", dtype);
+#define LN_GO(T, ITERS, ROWS)                                                                              \
+  ln_vec_kernel<T, ITERS, ROWS><<<ceil_div(ceil_div(M, ROWS), wpc), threads, 0, s>>>((const T*)x, gamma, beta, (T*)y, M, C, eps)
+#define LN_DISPATCH(T)                                                                                     \
+  if (C % 8 == 0 && C <= 512) LN_GO(T, 2, 4);                                                              \
+  else if (C % 8 == 0 && C <= 768) LN_GO(T, 3, 2);                                                         \
+  else if (C % 8 == 0 && C <= 1280) LN_GO(T, 5, 1);                                                        \
+  else ln_generic_kernel<T><<<ceil_div(M, wpc), threads, 0, s>>>((const T*)x, gamma, beta, (T*)y, M, C, eps)
+  if (dtype == C2D_F32) { LN_DISPATCH(float); }
+  else { LN_DISPATCH(bf16); }
+#undef LN_DISPATCH
+#undef LN_GO
   return check_launch("layer_norm");
 }
 

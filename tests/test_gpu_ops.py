@@ -123,6 +123,17 @@ def test_conv3x3_tcgen05(B, H, W, Cin, Cout):
     assert rel(y2, ys) < 1e-2            # tcgen05 vs FFMA on identical bf16 inputs
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (3, 16, 16, 1280, 1280), (1, 8, 8, 64, 32)])
+def test_conv3x3_stride2_tcgen05(B, H, W, Cin, Cout):
+    """Downsample2D conv: stride-2 gather through TMA element strides."""
+    x = rnd(B, H, W, Cin, dtype=BF16)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), BF16)
+    b = rnd(Cout, seed=2)
+    y = ops.conv3x3(x, w, b, stride=2, impl=ops.IMPL_TCGEN05)
+    ref = T.conv3x3(x, w, b, stride=2)
+    assert y.shape == ref.shape and rel(y, ref) < 1e-2
+
+
 def test_pack_conv():
     w = rnd(24, 16, 3, 3)
     assert torch.equal(ops.pack_conv3x3(w, F32), T.pack_conv3x3(w, F32))
