@@ -183,6 +183,21 @@ def run_ncu_step(args):
     print(json.dumps({"ncu_step": "done", "micro_batch": m}))
 
 
+def run_kernels(args):
+    """`--kernels`: per-kernel CUDA-event table of one eager UNet step (quick iteration aid)."""
+    import contextlib
+    from clap2diffusion_b200.pipeline import AudioToImagePipeline
+    dev = torch.device("cuda", 0)
+    with contextlib.redirect_stdout(sys.stderr):
+        pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16, with_vae=False)
+    agg = per_kernel_profile(pipe, args.micro_batch)
+    total = sum(a["ms"] for a in agg.values())
+    print(f"UNet step (batch {2 * args.micro_batch}) eager sum: {total:.3f} ms")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        tf = f"{a['flops'] / (a['ms'] * 1e-3) / 1e12:7.1f} TF/s" if a["flops"] else "            "
+        print(f"  {k:18s} {a['ms']:8.3f} ms  {100 * a['ms'] / total:5.1f}%  x{a['launches']:<4d} {tf}  {a['bytes'] / (a['ms'] * 1e-3) / 1e9:8.1f} GB/s")
+
+
 def run_ours(args):
     import contextlib
     import torch.distributed as dist
@@ -335,10 +350,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--micro-batch", type=int, default=8)
+    ap.add_argument("--kernels", action="store_true", help="print the per-kernel CUDA-event table of one UNet step")
     ap.add_argument("--ncu-step", action="store_true", help="profile one eager UNet step (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.ncu_step:
         run_ncu_step(args)
+    elif args.kernels:
+        run_kernels(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

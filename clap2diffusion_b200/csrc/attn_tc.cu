@@ -3,17 +3,22 @@
 // Used for the UNet's spatial self-attention (N = 4096/1024/256/64, d = 40/80/160, packed QKV views) and
 // for the text/audio cross-attention core (Nkv = 77/81, cached K/V views).
 //
-// One CTA = 128 queries of one (batch, head); keys are streamed in tiles of 128.
-//   warp 0      TMA producer: Q once, K (2 stages) and V (1 stage) tiles.  Each operand is a 4-D tensor map
-//               [B][N][heads][d]; boxes are 64 elements wide so columns >= d are zero-filled by TMA -- head
-//               dims 40 / 80 / 160 need no padding in memory and feed canonical 128B-swizzled smem tiles.
-//   warp 1      MMA issuer:  S = Q K^T   (M=128, N=128, K = ceil16(d); both operands K-major)      -> TMEM
-//                            O += P V    (M=128, N = ceil16(d), K=128; P K-major from smem, V MN-major) -> TMEM
-//   warps 2..5  softmax: thread = query row.  Two passes over S in TMEM (row max, then exp2 / row sum /
-//               bf16 P into swizzled smem), lazy rescale of the O accumulator (only when the running max
-//               moves by more than 2^8), final 1/l normalisation and bf16 store.
-// S (128 cols) and O (<=160 cols) live in TMEM; P goes through smem (generic-proxy writes + proxy fence).
-// For d <= 64 two CTAs fit per SM so one CTA's softmax overlaps the other's MMAs.
+// One CTA = 128 queries of one (batch, head); keys are streamed in tiles of 64.
+//   warp 0      TMA producer: Q once, K and V tiles through separate mbarrier rings.  Each operand is a 4-D
+//               tensor map [B][N][heads][d]; boxes are 64 elements wide so columns >= d are zero-filled by TMA --
+//               head dims 40 / 80 / 160 need no padding in memory and land as canonical 128B-swizzled tiles.
+//   warp 1      MMA issuer:  S[t&1] = Q K_t^T  (M=128, N=64, K = ceil16(d); both K-major)          -> TMEM
+//                            O    += P_t V_t   (M=128, N = ceil16(d), K=64; P K-major smem, V MN-major) -> TMEM
+//               S is double-buffered in TMEM and QK runs two tiles ahead of the softmax.
+//   warps 2..5  softmax: thread = query row.  ONE pass over S in the common case: p = exp2(s*scale - m_ref)
+//               against a LAGGING reference max; the largest probability is tracked on the packed bf16 bits,
+//               and only when it exceeds 2^8 is the tile redone with a new reference and the O accumulator
+//               rescaled in TMEM.  P goes to a double-buffered swizzled smem tile (generic-proxy writes +
+//               proxy fence).  Final 1/l normalisation and 16-byte bf16 stores.
+// For d <= 64 (S 2x64 + O <= 64 TMEM columns, ~97 KB smem) two CTAs share an SM.
+// Measured alternatives that were slower on B200 (kept out): S triple-buffering, row sums on the tensor core
+// (P x ones), 8 softmax warps with a per-key-half split -- the kernel is bounded by TMEM-read + MUFU.EX2
+// throughput (ncu: pipe_tc ~58 %, xu ~50 %), not by warp-level latency hiding.
 #include <float.h>
 
 #include "common.cuh"
@@ -26,27 +31,31 @@ using namespace tc;
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
-constexpr int AT_BQ = 128, AT_BK = 128, AT_THREADS = 192, AT_TILE = 128 * 128;   // 16 KB: 128 rows x 128 B
+constexpr int AT_BQ = 128, AT_BK = 64, AT_THREADS = 192;
+constexpr int AT_QTILE = 128 * 128;     // 128 rows x 128 B
+constexpr int AT_KTILE = 64 * 128;      // 64 rows  x 128 B
+constexpr int AT_SB = 2;                // S ring depth in TMEM
 
 struct AttnTcParams {
   bf16* o;
   int Nq, Nkv, d, npv;          // npv = ceil16(d): N extent of the PV MMA
+  int tmem_cols;                // power of two >= 2*64 + npv
   long long ldo, bso;
   float scale_log2;             // softmax scale * log2(e)
 };
 
 template <int NBLK>
 struct AtCfg {
-  static constexpr int Q_BYTES = NBLK * AT_TILE;
-  static constexpr int K_STAGES = 2;
+  static constexpr int KS = NBLK == 3 ? 2 : 3;               // K ring depth
+  static constexpr int VS = NBLK == 3 ? 2 : 3;               // V ring depth
+  static constexpr int Q_BYTES = NBLK * AT_QTILE;
+  static constexpr int KV_BYTES = NBLK * AT_KTILE;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + K_STAGES * Q_BYTES;
-  static constexpr int OFF_P = OFF_V + Q_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * AT_TILE;
+  static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + VS * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * AT_QTILE;       // P: 2 x [128 rows x 64 keys] bf16
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_COLS = NBLK <= 2 ? 256 : 512;
-  static constexpr int O_COL = 128;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -56,23 +65,23 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 template <int NBLK>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT_THREADS, NBLK == 1 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using Cfg = AtCfg<NBLK>;
+  constexpr int KS = Cfg::KS, VS = Cfg::VS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;
-  uint64_t* s_empty = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;  // = PV(j) retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* k_full = bars + 1;      // [3]
+  uint64_t* k_empty = bars + 4;     // [3]
+  uint64_t* v_full = bars + 7;      // [3]
+  uint64_t* v_empty = bars + 10;    // [3]
+  uint64_t* s_full = bars + 13;     // [2]
+  uint64_t* p_full = bars + 15;     // [2]
+  uint64_t* p_empty = bars + 17;    // [2]  PV(t) retired (P[t&1] reusable, O up to date)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -81,75 +90,84 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(s_empty, 128);
-    mbar_init(p_full, 128); mbar_init(p_empty, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc_n(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + Cfg::O_COL;
+  const uint32_t tmem_o = tmem_base + AT_SB * AT_BK;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(smem + Cfg::OFF_Q + blk * AT_TILE, &tmQ, q_full, blk * 64, h, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t u = (uint32_t)(j >> 1);
-        mbar_wait(&k_empty[s], (u & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&k_full[s], Cfg::Q_BYTES);
+      for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(smem + Cfg::OFF_Q + blk * AT_QTILE, &tmQ, q_full, blk * 64, h, q0, b);
+      for (int t = 0; t < ntiles; ++t) {
+        {
+          const int s = t % KS;
+          mbar_wait(&k_empty[s], ((uint32_t)(t / KS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&k_full[s], Cfg::KV_BYTES);
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(smem + Cfg::OFF_K + (s * NBLK + blk) * AT_TILE, &tmK, &k_full[s], blk * 64, h, j * AT_BK, b);
-        mbar_wait(v_empty, ((uint32_t)j & 1u) ^ 1u);
-        mbar_arrive_expect_tx(v_full, Cfg::Q_BYTES);
+          for (int blk = 0; blk < NBLK; ++blk)
+            tma_load_4d(smem + Cfg::OFF_K + (s * NBLK + blk) * AT_KTILE, &tmK, &k_full[s], blk * 64, h, t * AT_BK, b);
+        }
+        {
+          const int s = t % VS;
+          mbar_wait(&v_empty[s], ((uint32_t)(t / VS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&v_full[s], Cfg::KV_BYTES);
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(smem + Cfg::OFF_V + blk * AT_TILE, &tmV, v_full, blk * 64, h, j * AT_BK, b);
+          for (int blk = 0; blk < NBLK; ++blk)
+            tma_load_4d(smem + Cfg::OFF_V + (s * NBLK + blk) * AT_KTILE, &tmV, &v_full[s], blk * 64, h, t * AT_BK, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_qk = make_idesc_bf16(128, AT_BK, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, p.npv, 0, 1);          // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q);
-      const uint32_t p_addr = smem_u32(smem + Cfg::OFF_P);
-      const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V);
       const int ksteps = (p.d + 15) >> 4;
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (uint32_t)(j >> 1) & 1u);
-        if (j > 0) mbar_wait(s_empty, (uint32_t)(j - 1) & 1u);
+      auto issue_qk = [&](int t) {
+        const int s = t % KS;
+        mbar_wait(&k_full[s], (uint32_t)(t / KS) & 1u);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + s * NBLK * AT_TILE);
+        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + s * Cfg::KV_BYTES);
+        const uint32_t tmem_s = tmem_base + (uint32_t)(t & 1) * AT_BK;
         for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 2) * AT_TILE + (uint32_t)(kk & 3) * 32;
-          umma_f16(tmem_s, make_desc_k_sw128(q_addr + off), make_desc_k_sw128(k_addr + off), idesc_qk, kk > 0 ? 1u : 0u);
+          const uint32_t koff = (uint32_t)(kk & 3) * 32;
+          umma_f16(tmem_s, make_desc_k_sw128(q_addr + (uint32_t)(kk >> 2) * AT_QTILE + koff),
+                   make_desc_k_sw128(k_addr + (uint32_t)(kk >> 2) * AT_KTILE + koff), idesc_qk, kk > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[t & 1]);
         umma_commit(&k_empty[s]);
-        // ---- O += P V
-        mbar_wait(p_full, (uint32_t)j & 1u);
-        mbar_wait(v_full, (uint32_t)j & 1u);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (ntiles > 1) issue_qk(1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int pb = j & 1, vs = j % VS;
+        mbar_wait(&p_full[pb], (uint32_t)(j >> 1) & 1u);     // P(j) written, S(j) consumed
+        mbar_wait(&v_full[vs], (uint32_t)(j / VS) & 1u);
         tc_fence_after();
+        const uint32_t p_addr = smem_u32(smem + Cfg::OFF_P + pb * AT_QTILE);
+        const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V + vs * Cfg::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < AT_BK / 16; ++kk) {
-          const uint64_t a_desc = make_desc_k_sw128(p_addr + (uint32_t)(kk >> 2) * AT_TILE + (uint32_t)(kk & 3) * 32);
-          // V tile: [128 keys][64-col blocks]; 16 keys = 2 groups of 8 rows (SBO = 1024 B), col blocks 16 KB apart (LBO)
-          const uint64_t b_desc = make_desc_mn_sw128(v_addr + (uint32_t)kk * 2048, AT_TILE, 1024);
-          umma_f16(tmem_o, a_desc, b_desc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          // V tile: [64 keys][64-col blocks]; 16 keys = 2 groups of 8 rows (SBO = 1024 B), col blocks 8 KB apart (LBO)
+          umma_f16(tmem_o, make_desc_k_sw128(p_addr + (uint32_t)kk * 32),
+                   make_desc_mn_sw128(v_addr + (uint32_t)kk * 2048, AT_KTILE, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(p_empty);
-        umma_commit(v_empty);
+        umma_commit(&p_empty[pb]);
+        umma_commit(&v_empty[vs]);
+        // refill the S buffer that softmax(j) released.  (After PV(j), never before: the producer may need
+        // v_empty from PV(j) before it can reach K(j+2).)
+        if (j + AT_SB < ntiles) issue_qk(j + AT_SB);
       }
     }
   } else {
@@ -157,98 +175,113 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    uint8_t* p_row = smem + Cfg::OFF_P + row * 128;
     const int rsw = row & 7;
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
+      const int pb = j & 1;
       const int kvalid = min(AT_BK, p.Nkv - j * AT_BK);
-      mbar_wait(s_full, (uint32_t)j & 1u);
+      const uint32_t tmem_s = tmem_base + (uint32_t)pb * AT_BK + lane_off;
+      uint8_t* p_row = smem + Cfg::OFF_P + pb * AT_QTILE + row * 128;
+      mbar_wait(&s_full[pb], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       if (j == 0) {
         // first tile: the reference max must be known before any exponential is taken
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t r[32];
-          tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
+          tmem_ld_32x32(tmem_s + c * 32, r);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
         m_ref = mx * p.scale_log2;
-      } else {
-        mbar_wait(p_empty, (uint32_t)(j - 1) & 1u);     // PV(j-1) retired: P smem free, O complete
       }
-      // ---- single pass in the common case: p = exp2(s * scale_log2 - m_ref) against the LAGGING reference max,
-      //      tracking the tile max on the side.  Only if some row's max moved by more than 2^8 is the tile redone
-      //      with the new reference and the O accumulator rescaled (rare after the first tiles).
-      float sum, mx;
+      if (j >= 2) mbar_wait(&p_empty[pb], (uint32_t)((j - 2) >> 1) & 1u);     // PV(j-2) retired: P[pb] is free
+      float sum;
       float alpha = 1.f;
       bool redo = false;
       for (;;) {
         sum = 0.f;
-        mx = -INFINITY;
+        uint32_t pmax2 = 0u;           // running max of the packed bf16 probabilities (p >= 0: bit patterns are ordered)
         uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tmem_s + lane_off, ra);
+        tmem_ld_32x32(tmem_s, ra);
+        tmem_ld_32x32(tmem_s + 32, rb);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&r)[32] = (c & 1) ? rb : ra;
-          uint32_t (&rn)[32] = (c & 1) ? ra : rb;
-          tmem_ld_wait();
-          if (c < 3) tmem_ld_32x32(tmem_s + lane_off + (c + 1) * 32, rn);    // prefetch next chunk
+        for (int c = 0; c < 2; ++c) {
+          uint32_t (&r)[32] = c ? rb : ra;
           uint32_t packed[16];
           if (kvalid == AT_BK) {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
-              mx = fmaxf(mx, fmaxf(s0, s1));
-              __nv_bfloat162 hb = __floats2bfloat162_rn(ex2f(fmaf(s0, p.scale_log2, -m_ref)), ex2f(fmaf(s1, p.scale_log2, -m_ref)));
-              sum += __low2float(hb) + __high2float(hb);      // what the tensor core will actually see
+              const float p0 = ex2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref));
+              const float p1 = ex2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref));
+              sum += p0 + p1;
+              __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+              pmax2 = __vmaxu2(pmax2, packed[i >> 1]);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const bool v0 = c * 32 + i < kvalid, v1 = c * 32 + i + 1 < kvalid;
-              const float s0 = v0 ? __uint_as_float(r[i]) : -INFINITY, s1 = v1 ? __uint_as_float(r[i + 1]) : -INFINITY;
-              mx = fmaxf(mx, fmaxf(s0, s1));
-              __nv_bfloat162 hb = __floats2bfloat162_rn(v0 ? ex2f(fmaf(s0, p.scale_log2, -m_ref)) : 0.f,
-                                                        v1 ? ex2f(fmaf(s1, p.scale_log2, -m_ref)) : 0.f);
-              sum += __low2float(hb) + __high2float(hb);
+              const float p0 = (c * 32 + i < kvalid) ? ex2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_ref)) : 0.f;
+              const float p1 = (c * 32 + i + 1 < kvalid) ? ex2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_ref)) : 0.f;
+              sum += p0 + p1;
+              __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+              pmax2 = __vmaxu2(pmax2, packed[i >> 1]);
             }
           }
-          // 32 keys = 4 chunks of 16 B; key block (64 keys) = c >> 1, chunk index within the 128 B row = (c & 1) * 4 + q
-          uint8_t* blk = p_row + (c >> 1) * AT_TILE;
+          // 32 keys = 4 chunks of 16 B; chunk index within the 128 B row = c * 4 + q, XOR-swizzled by the row
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int chunk = ((c & 1) * 4 + q) ^ rsw;
-            *reinterpret_cast<uint4*>(blk + (chunk << 4)) =
+            const int chunk = (c * 4 + q) ^ rsw;
+            *reinterpret_cast<uint4*>(p_row + (chunk << 4)) =
                 make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
           }
         }
         if (redo) break;
-        mx *= p.scale_log2;
-        const bool need = mx > m_ref + 8.0f;
+        // largest probability of the row, as bf16 bits: > 2^8 means the row max ran ahead of the reference
+        const uint32_t pm = max(pmax2 & 0xFFFFu, pmax2 >> 16);
+        const bool need = pm > 0x4380u;                      // bf16(256.0)
         if (!__any_sync(0xffffffffu, need)) break;
+        // new reference for the rows that moved: m_ref + log2(pmax); if the exponential overflowed, take the exact max
+        float mnew = m_ref + __log2f(__uint_as_float(pm << 16));
+        if (__any_sync(0xffffffffu, need && pm >= 0x7F80u)) {
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_s + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+          mnew = mx * p.scale_log2;
+        }
         if (need) {
-          alpha = ex2f(m_ref - mx);
-          m_ref = mx;
+          alpha = ex2f(m_ref - mnew);
+          m_ref = mnew;
         }
         redo = true;
       }
       if (redo && j > 0) {
-        // warp-collective rescale of the O accumulator (rows that did not move use alpha = 1)
+        // warp-collective rescale of the O accumulator (rows that did not move use alpha = 1); every PV issued so
+        // far must have retired first
+        mbar_wait(&p_empty[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1u);
+        tc_fence_after();
         for (int c = 0; c < p.npv; c += 16) {
-          uint32_t r[16];
-          tmem_ld_32x16(tmem_o + lane_off + c, r);
+          uint32_t o[16];
+          tmem_ld_32x16(tmem_o + lane_off + c, o);
           tmem_ld_wait();
           uint32_t lo[8], hi[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            lo[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            hi[i] = __float_as_uint(__uint_as_float(r[8 + i]) * alpha);
+            lo[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            hi[i] = __float_as_uint(__uint_as_float(o[8 + i]) * alpha);
           }
           tmem_st_32x8(tmem_o + lane_off + c, lo);
           tmem_st_32x8(tmem_o + lane_off + c + 8, hi);
@@ -257,12 +290,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       l_run = l_run * alpha + sum;
       tc_fence_before();
-      mbar_arrive(s_empty);           // S(j) fully read: QK(j+1) may overwrite it
       fence_proxy_async();            // P writes (generic proxy) -> visible to tcgen05.mma (async proxy)
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[pb]);       // also tells the MMA warp that S[pb] has been consumed
     }
     // ---- epilogue: O / l -> bf16 -> global
-    mbar_wait(p_empty, (uint32_t)(ntiles - 1) & 1u);
+    mbar_wait(&p_empty[(ntiles - 1) & 1], (uint32_t)((ntiles - 1) >> 1) & 1u);
     tc_fence_after();
     const int qrow = q0 + row;
     const float inv = 1.f / l_run;
@@ -290,24 +322,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc_n(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool attention_tc_supported(const AttnParams& p, int B) {
-  (void)B;
   return p.mask == nullptr && p.d % 8 == 0 && p.d >= 16 && p.d <= 192 && p.ldq % 8 == 0 && p.ldk % 8 == 0 &&
          p.ldv % 8 == 0 && p.ldo % 8 == 0 && p.bsq % 8 == 0 && p.bsk % 8 == 0 && p.bsv % 8 == 0 && p.bso % 8 == 0 &&
          (B == 1 || (p.bsq > 0 && p.bsk > 0 && p.bsv > 0)) && al16(p.q) && al16(p.k) && al16(p.v) && al16(p.o) &&
          p.Nq >= 1 && p.Nkv >= 1;
 }
 
-static int make_head_tmap(CUtensorMap* m, const void* base, int d, int heads, int N, int B, long long ld, long long bs) {
+static int make_head_tmap(CUtensorMap* m, const void* base, int d, int heads, int N, int B, long long ld, long long bs,
+                          int box_rows) {
   uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
   uint64_t st[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)(B > 1 ? bs : (long long)N * ld) * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return make_tmap_bf16(m, base, 4, dims, st, box);
 }
 
@@ -331,16 +363,18 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 
 int attention_tc(const AttnParams& p, int B, cudaStream_t s) {
   CUtensorMap tq, tk, tv;
-  int rc = make_head_tmap(&tq, p.q, p.d, p.heads, p.Nq, B, p.ldq, p.bsq);
+  int rc = make_head_tmap(&tq, p.q, p.d, p.heads, p.Nq, B, p.ldq, p.bsq, AT_BQ);
   if (rc) return rc;
-  rc = make_head_tmap(&tk, p.k, p.d, p.heads, p.Nkv, B, p.ldk, p.bsk);
+  rc = make_head_tmap(&tk, p.k, p.d, p.heads, p.Nkv, B, p.ldk, p.bsk, AT_BK);
   if (rc) return rc;
-  rc = make_head_tmap(&tv, p.v, p.d, p.heads, p.Nkv, B, p.ldv, p.bsv);
+  rc = make_head_tmap(&tv, p.v, p.d, p.heads, p.Nkv, B, p.ldv, p.bsv, AT_BK);
   if (rc) return rc;
   AttnTcParams ap;
   ap.o = reinterpret_cast<bf16*>(p.o);
   ap.Nq = p.Nq; ap.Nkv = p.Nkv; ap.d = p.d; ap.npv = (p.d + 15) & ~15;
   ap.ldo = p.ldo; ap.bso = p.bso;
+  const int need = AT_SB * AT_BK + ap.npv;
+  ap.tmem_cols = need <= 256 ? 256 : 512;
   ap.scale_log2 = p.scale * 1.4426950408889634f;
   const int nblk = (p.d + 63) / 64;
   if (nblk == 1) return launch_attn_tc<1>(tq, tk, tv, ap, p.heads, B, s);

@@ -87,25 +87,8 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 256 + 2 * BN * 4 + 1024;   // + barriers + bias/rowvec + slack
 };
-
-__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&v)[32], bool vec_ok, int nvalid) {
-  if (vec_ok && nvalid >= 32) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 r;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[g * 8 + 2 * i], v[g * 8 + 2 * i + 1]);
-      *reinterpret_cast<uint4*>(dst + g * 8) = r;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
-  }
-}
 
 template <int BN, bool CONV, bool GEGLU>
 __global__ void __launch_bounds__(TC_THREADS)
@@ -187,78 +170,133 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers (+bias, +row vector, activation / GEGLU gate) -> fp32 staging tile in the (now idle)
+    // pipeline smem -> coalesced pass: 16-byte residual loads and bf16 stores along rows.  Each warp stages
+    // and drains only its own 32 rows, so a __syncwarp is the only synchronisation.
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    constexpr int NOUT = GEGLU ? BN / 2 : BN;         // output columns this CTA produces
+    constexpr int PITCH = NOUT + 4;                   // floats; rows stay 16 B aligned, 16 B writes conflict-free
+    // while the main loop runs: this CTA's slice of bias (+ time-embedding row vector when it is shared by the
+    // whole tile) -> smem, so the drain below issues no dependent global loads for them
+    float* s_bias = reinterpret_cast<float*>(smem + TC_STAGES * Cfg::STAGE_BYTES + 256);
+    const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
+    {
+      const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
+      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        const int n = n0 + j;
+        float b = 0.f;
+        if (n < p.N) {
+          if (p.bias) b = __ldg(p.bias + n);
+          if (rv0) b += __ldg(rv0 + n);
+        }
+        s_bias[j] = b;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * PITCH;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* rv = (p.rowvec && row_ok) ? p.rowvec + (long long)(m / p.rows_per_vec) * p.N : nullptr;
-    if (!GEGLU) {
-      const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-      const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    {
+      const int m = m0 + q * 32 + lane;
+      const float* rv = (p.rowvec && !rv_shared && m < p.M) ? p.rowvec + (long long)(m / p.rows_per_vec) * p.N : nullptr;
+      float* srow = stage + (size_t)lane * PITCH;
+      if (!GEGLU) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int n = n0 + c * 32;
-        const int nvalid = p.N - n;
-        if (row_ok && nvalid > 0) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          const int n = n0 + c * 32;
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(p.bias + n + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
+            v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
           }
           if (rv) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __ldg(rv + n + j);
+            for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rv + n + j);
           }
           if (p.act != C2D_ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
           }
-          if (p.residual) {
-            const bf16* rp = p.residual + (long long)m * p.ldr + n;
-            if (vec_r && nvalid >= 32) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float f[8];
-                Vec8<bf16>::load(rp + g * 8, f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[g * 8 + j] += f[j];
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
-            }
-          }
-          store_bf16x32(p.y + (long long)m * p.ldy + n, v, vec_y, nvalid);
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
-      }
-    } else {
-      // GEGLU: tile columns [0,64) = a, [64,128) = gate for output columns n0/2 + [0,64)
-      const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-      const int F = p.N >> 1;
+      } else {
+        // GEGLU: tile columns [0,64) = a, [64,128) = gate for output columns n0/2 + [0,64)
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ra[32], rg[32];
-        tmem_ld_32x32(t_row + c * 32, ra);
-        tmem_ld_32x32(t_row + 64 + c * 32, rg);
-        tmem_ld_wait();
-        const int fo = (n0 >> 1) + c * 32;
-        const int nvalid = F - fo;
-        if (row_ok && nvalid > 0) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ra[32], rg[32];
+          tmem_ld_32x32(t_row + c * 32, ra);
+          tmem_ld_32x32(t_row + 64 + c * 32, rg);
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(ra[j]), g = __uint_as_float(rg[j]);
-            if (p.bias) { a += __ldg(p.bias + n0 + c * 32 + j); g += __ldg(p.bias + n0 + 64 + c * 32 + j); }
+            const float a = __uint_as_float(ra[j]) + s_bias[c * 32 + j];
+            const float g = __uint_as_float(rg[j]) + s_bias[64 + c * 32 + j];
             v[j] = a * gelu_erf(g);
           }
-          store_bf16x32(p.y + (long long)m * p.ldy + fo, v, vec_y, nvalid);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    }
+    __syncwarp();
+    {
+      const int ncols = GEGLU ? (p.N >> 1) : p.N;            // logical output width
+      const int nbase = GEGLU ? (n0 >> 1) : n0;
+      const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+      const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+      constexpr int GROUPS = NOUT / 8;                        // 8-column groups per row
+      constexpr int ITERS = GROUPS;                           // 32 rows * GROUPS groups / 32 lanes
+      constexpr int UNR = (ITERS % 5 == 0) ? 5 : 4;           // residual loads kept in flight per lane
+      static_assert(ITERS % UNR == 0, "epilogue unroll");
+#pragma unroll 1
+      for (int it0 = 0; it0 < ITERS; it0 += UNR) {
+        uint4 res[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {                       // (1) all residual loads of the batch first
+          const int idx = lane + 32 * (it0 + u);
+          const int rr = idx / GROUPS, g = idx - rr * GROUPS;
+          const int m = m0 + q * 32 + rr, n = nbase + g * 8;
+          ok[u] = m < p.M && n < ncols;
+          res[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u] && vec_r && ncols - n >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {                       // (2) drain
+          if (!ok[u]) continue;
+          const int idx = lane + 32 * (it0 + u);
+          const int rr = idx / GROUPS, g = idx - rr * GROUPS;
+          const int m = m0 + q * 32 + rr, n = nbase + g * 8;
+          const float* sp = stage + (size_t)rr * PITCH + g * 8;
+          const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
+          float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          const int nvalid = ncols - n;
+          bf16* yp = p.y + (long long)m * p.ldy + n;
+          if (p.residual) {
+            if (vec_r && nvalid >= 8) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            } else {
+              const bf16* rp = p.residual + (long long)m * p.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (vec_y && nvalid >= 8) {
+            Vec8<bf16>::store(yp, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(v[j]);
+          }
         }
       }
     }
