@@ -17,9 +17,14 @@ __device__ __forceinline__ void gn_load(const T* __restrict__ x, const T* __rest
   else Vec8<T>::load(x2 + row * C2 + (c - C1), f);
 }
 
+// SiLU: accurate in the fp32 parity mode; MUFU ex2 + rcp in bf16 mode (the result is rounded to bf16 anyway)
+template <typename T> __device__ __forceinline__ float gn_silu(float v);
+template <> __device__ __forceinline__ float gn_silu<float>(float v) { return silu_acc(v); }
+template <> __device__ __forceinline__ float gn_silu<bf16>(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+
 // grid: (slabs, B).  Each CTA reduces `rows_per_cta` rows of one image into stats[b][g][{sum,sumsq}].
 template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __restrict__ stats, int HW, int C1, int C2,
                 int groups, int rows_per_cta) {
   const int C = C1 + C2, nvec = C >> 3, cpg = C / groups;
@@ -35,29 +40,36 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
   if (my_rl < rows_in_flight) {
-    // GN_UNROLL independent 128-bit loads in flight per thread (memory-level parallelism)
-    for (int r = r0 + my_rl; r < r1; r += GN_UNROLL * rows_in_flight) {
-      float f[GN_UNROLL][GN_MAX_ITERS][8];
+    const bool has2 = my_vec + nvec_eff < nvec;            // second channel vector (only when C > 2048)
+    int r = r0 + my_rl;
+    // GN_UNROLL independent 128-bit loads in flight per thread, issued unconditionally (memory-level parallelism)
+    for (; r + (GN_UNROLL - 1) * rows_in_flight < r1; r += GN_UNROLL * rows_in_flight) {
+      float f[GN_UNROLL][8];
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
-        const int rr = r + u * rows_in_flight;
-        const long long row = (long long)b * HW + rr;
-#pragma unroll
-        for (int it = 0; it < GN_MAX_ITERS; ++it) {
-          const int vec = my_vec + it * nvec_eff;
-          if (rr < r1 && vec < nvec) gn_load<T>(x, x2, row, vec * 8, C1, C2, f[u][it]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[u][it][j] = 0.f;
-          }
-        }
-      }
+      for (int u = 0; u < GN_UNROLL; ++u) gn_load<T>(x, x2, (long long)b * HW + r + u * rows_in_flight, my_vec * 8, C1, C2, f[u]);
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u)
 #pragma unroll
-        for (int it = 0; it < GN_MAX_ITERS; ++it)
+        for (int j = 0; j < 8; ++j) { acc[0][j] += f[u][j]; acq[0][j] += f[u][j] * f[u][j]; }
+      if (has2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { acc[it][j] += f[u][it][j]; acq[it][j] += f[u][it][j] * f[u][it][j]; }
+        for (int u = 0; u < GN_UNROLL; ++u) gn_load<T>(x, x2, (long long)b * HW + r + u * rows_in_flight, (my_vec + nvec_eff) * 8, C1, C2, f[u]);
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[1][j] += f[u][j]; acq[1][j] += f[u][j] * f[u][j]; }
+      }
+    }
+    for (; r < r1; r += rows_in_flight) {
+      float f[8];
+      gn_load<T>(x, x2, (long long)b * HW + r, my_vec * 8, C1, C2, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acq[0][j] += f[j] * f[j]; }
+      if (has2) {
+        gn_load<T>(x, x2, (long long)b * HW + r, (my_vec + nvec_eff) * 8, C1, C2, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[1][j] += f[j]; acq[1][j] += f[j] * f[j]; }
+      }
     }
   }
   // per-(row lane, channel) fp32 partials -> smem, then one thread per group folds them in double
@@ -92,7 +104,7 @@ gn_stats_kernel(const T* __restrict__ x, const T* __restrict__ x2, double* __res
 }
 
 template <typename T>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 3)
 gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const double* __restrict__ stats, T* __restrict__ y,
                 T* __restrict__ raw, int HW, int C1, int C2, int groups, float eps, int silu, int rows_per_cta) {
@@ -129,27 +141,34 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, const float* 
     float a[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] = s_a[c + j]; sh[j] = s_b[c + j]; }
-    for (int r = r0 + my_rl; r < r1; r += GN_UNROLL * rows_in_flight) {
+    int r = r0 + my_rl;
+    for (; r + (GN_UNROLL - 1) * rows_in_flight < r1; r += GN_UNROLL * rows_in_flight) {
       float f[GN_UNROLL][8];
 #pragma unroll
-      for (int u = 0; u < GN_UNROLL; ++u) {
-        const int rr = r + u * rows_in_flight;
-        if (rr < r1) gn_load<T>(x, x2, (long long)b * HW + rr, c, C1, C2, f[u]);
-      }
+      for (int u = 0; u < GN_UNROLL; ++u) gn_load<T>(x, x2, (long long)b * HW + r + u * rows_in_flight, c, C1, C2, f[u]);
 #pragma unroll
       for (int u = 0; u < GN_UNROLL; ++u) {
-        const int rr = r + u * rows_in_flight;
-        if (rr < r1) {
-          const long long row = (long long)b * HW + rr;
-          if (raw) Vec8<T>::store(raw + row * C + c, f[u]);
+        const long long row = (long long)b * HW + r + u * rows_in_flight;
+        if (raw) Vec8<T>::store(raw + row * C + c, f[u]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = f[u][j] * a[j] + sh[j];
-            f[u][j] = silu ? silu_acc(v) : v;
-          }
-          Vec8<T>::store(y + row * C + c, f[u]);
+        for (int j = 0; j < 8; ++j) {
+          const float v = f[u][j] * a[j] + sh[j];
+          f[u][j] = silu ? gn_silu<T>(v) : v;
         }
+        Vec8<T>::store(y + row * C + c, f[u]);
       }
+    }
+    for (; r < r1; r += rows_in_flight) {
+      const long long row = (long long)b * HW + r;
+      float f[8];
+      gn_load<T>(x, x2, row, c, C1, C2, f);
+      if (raw) Vec8<T>::store(raw + row * C + c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = f[j] * a[j] + sh[j];
+        f[j] = silu ? gn_silu<T>(v) : v;
+      }
+      Vec8<T>::store(y + row * C + c, f);
     }
   }
 }

@@ -119,3 +119,20 @@ def test_batch_invariance_and_euler(W, pipe32, pipe16):
     got = pipe16.generate(clap[:1], cc[:1], cu[:1], nz[:1], steps=50, scheduler="euler", decode=False, trace=True, max_steps=2)
     for i in range(2):
         assert rel_l2(_t(got["trace"][i]), ref["latents"][i]) <= 1e-2
+
+
+def test_inference_cli_end_to_end(tmp_path):
+    """Drop-in CLI (reference scripts/inference.py:182-214): same flags, writes a real 512x512 image."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("c2d_inference", os.path.join(os.path.dirname(__file__), "..", "scripts", "inference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "out.png"
+    mod.main(["--audio", "synthetic:3", "--text", "a beach", "--output", str(out), "--checkpoint_dir", str(tmp_path),
+              "--steps", "4", "--cfg_scale", "7.5", "--seed", "1"])
+    from PIL import Image
+    im = Image.open(out)
+    assert im.size == (512, 512) and im.mode == "RGB"
+    a = np.asarray(im).astype(np.float32)
+    assert a.std() > 1.0            # not a constant image

@@ -235,3 +235,16 @@ def test_vae_host_logic_vs_oracle(W):
         img = VAEDecoder(W["vae"], device="cpu", dtype=torch.float32).decode(z)
     assert tuple(img.shape) == (1, 3, 64, 64)
     assert rel_l2(img, ref) < 2e-5
+
+
+def test_inference_cli_surface():
+    """Same flags / defaults and class API as the reference's scripts/inference.py (:21-214)."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(__file__), "..", "scripts", "inference.py")).read()
+    for flag in ("--audio", "--text", "--output", "--checkpoint_dir", "--steps", "--cfg_scale", "--seed", "--no_hierarchical"):
+        assert f'"{flag}"' in src, flag
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "AudioToImageInference"][0]
+    methods = {n.name for n in cls.body if isinstance(n, ast.FunctionDef)}
+    assert {"load_models", "load_audio", "extract_clap_embedding", "apply_normalization", "generate", "batch_generate"} <= methods
