@@ -13,6 +13,7 @@
 // residual -> bf16 global stores).  3-stage mbarrier ring; 2 CTAs per SM so one CTA's epilogue overlaps
 // the other's main loop.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -327,6 +328,282 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
+
+// =====================================================================================================
+// Persistent variant: one CTA per SM loops over output tiles; the fp32 accumulator is DOUBLE-BUFFERED in
+// TMEM so the epilogue of tile i (TMEM -> regs -> smem -> coalesced global) overlaps the main loop of tile
+// i+1, and the TMA producer runs ahead across tile boundaries through a deeper smem ring.  Removes the
+// per-tile prologue (TMEM alloc, barrier init, pipeline fill) that dominated the short-K projections.
+// =====================================================================================================
+template <int BN, int STAGES>
+struct Tc2Cfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns between accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int EPI_PITCH = 36;                                          // floats per staged row (32 + pad)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BIAS = OFF_EPI + EPI_BYTES;                          // 2 x BN floats
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+template <int BN, int STAGES, bool CONV, bool GEGLU>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                const int num_tiles, const int num_n) {
+  using Cfg = Tc2Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;       // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;           // [2] accumulator drained (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (runs ahead across tiles) =====================
+      uint32_t kbc = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
+        int b0 = 0, y0 = 0, x0 = 0;
+        if (CONV) {
+          b0 = m0 / p.HW;
+          const int rem = m0 - b0 * p.HW;
+          y0 = rem / p.W;
+          x0 = rem - y0 * p.W;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
+          const int s = kbc % STAGES;
+          mbar_wait(&empty[s], ((kbc / STAGES) & 1u) ^ 1u);
+          uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          if (CONV) {
+            const int tap = kb / p.cblocks;
+            const int c0 = (kb - tap * p.cblocks) * TC_BK;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
+            tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
+          } else {
+            tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+            tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
+      uint32_t kbc = 0, it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(&tempty[buf], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
+          const int s = kbc % STAGES;
+          mbar_wait(&full[s], (kbc / STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint64_t a_desc = make_desc_k_sw128(a_addr);
+          const uint64_t b_desc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_f16(acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5), overlapped with the next tile's main loop =====================
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + (size_t)q * 32 * Cfg::EPI_PITCH;
+    const int ncols = GEGLU ? (p.N >> 1) : p.N;
+    const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+    const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
+      const int nbase = GEGLU ? (n0 >> 1) : n0;
+      // this tile's bias slice (+ the row vector when the whole tile shares one) -> smem
+      const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
+      float* sb = s_bias + buf * BN;
+      {
+        const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
+        for (int j = threadIdx.x - 64; j < BN; j += 128) {
+          const int n = n0 + j;
+          float bv = 0.f;
+          if (n < p.N) {
+            if (p.bias) bv = __ldg(p.bias + n);
+            if (rv0) bv += __ldg(rv0 + n);
+          }
+          sb[j] = bv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tfull[buf], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      constexpr int NCHUNK = GEGLU ? 2 : BN / 32;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        // ---- TMEM -> registers -> (+bias, activation | GEGLU gate) -> per-warp fp32 staging [32 rows][32 cols]
+        float v[32];
+        if (!GEGLU) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          if (c == NCHUNK - 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); }     // accumulator fully read
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[c * 32 + j];
+          if (p.rowvec && !rv_shared) {
+            const int m = m0 + q * 32 + lane;
+            if (m < p.M) {
+              const float* rv = p.rowvec + (long long)(m / p.rows_per_vec) * p.N + n0 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n0 + c * 32 + j < p.N) v[j] += __ldg(rv + j);
+            }
+          }
+          if (p.act != C2D_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+        } else {
+          uint32_t ra[32], rg[32];
+          tmem_ld_32x32(t_row + c * 32, ra);
+          tmem_ld_32x32(t_row + 64 + c * 32, rg);
+          tmem_ld_wait();
+          if (c == NCHUNK - 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = __uint_as_float(ra[j]) + sb[c * 32 + j];
+            const float g = __uint_as_float(rg[j]) + sb[64 + c * 32 + j];
+            v[j] = a * gelu_erf(g);
+          }
+        }
+        float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        // ---- coalesced drain: 32 rows x 4 groups of 8 columns; residual loads of all 4 items issued first
+        uint4 res[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = u * 8 + (lane >> 2), g = lane & 3;
+          const int m = m0 + q * 32 + rr, n = nbase + c * 32 + g * 8;
+          ok[u] = m < p.M && n < ncols;
+          res[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u] && vec_r && ncols - n >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const int rr = u * 8 + (lane >> 2), g = lane & 3;
+          const int m = m0 + q * 32 + rr, n = nbase + c * 32 + g * 8;
+          const float* sp = stage + (size_t)rr * Cfg::EPI_PITCH + g * 8;
+          const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
+          float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          const int nvalid = ncols - n;
+          bf16* yp = p.y + (long long)m * p.ldy + n;
+          if (p.residual) {
+            if (vec_r && nvalid >= 8) {
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res[u]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); o[2 * j] += f.x; o[2 * j + 1] += f.y; }
+            } else {
+              const bf16* rp = p.residual + (long long)m * p.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (j < nvalid) o[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (vec_y && nvalid >= 8) {
+            Vec8<bf16>::store(yp, o);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES, bool CONV, bool GEGLU>
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN, STAGES>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "persistent GEMM smem");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return C2D_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int num_n = ceil_div(p.N, BN);
+  const int num_tiles = num_n * ceil_div(p.M, TC_BM);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p, num_tiles, num_n);
+  return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
+}
+
+// Kernel selection.  Measured on B200 (tools/bench_shapes.py): the persistent kernel wins on the GEGLU projection
+// (N = 8C, short K: +20 %), the two-CTA-per-SM kernel wins elsewhere (two MMA issuers hide each other's
+// barrier round trips).  C2D_GEMM=legacy | persistent forces one of them for A/B runs.
+static int gemm_mode() {           // 0 = auto, 1 = legacy, 2 = persistent
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_GEMM");
+    v = !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 'p' ? 2 : 0));
+  }
+  return v;
+}
+static bool use_persistent(bool geglu = false) {
+  const int m = gemm_mode();
+  return m == 2 || (m == 0 && geglu);
+}
+
+// tile width: widest tile that still yields at least one tile per SM, else 64 (more CTAs, deeper ring)
+static int pick_bn(int M, int N) {
+  const int mt = ceil_div(M, TC_BM);
+  const int wide = (N % 160 == 0) ? 160 : 128;
+  if (mt * ceil_div(N, wide) >= num_sms() || N <= 64) return wide;
+  return 64;
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool linear_tc_supported(const void* x, const void* w, int M, int N, int K, int ldx) {
@@ -338,7 +615,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
               cudaStream_t s) {
   C2D_REQUIRE(linear_tc_supported(x, w, M, N, K, ldx),
               "linear_tc: needs bf16, K %% 8 == 0, ldx %% 8 == 0, 16B-aligned x/w (M=%d N=%d K=%d ldx=%d)", M, N, K, ldx);
-  const int BN = geglu ? 128 : ((N % 160 == 0) ? 160 : 128);
+  const int BN = geglu ? 128 : (use_persistent(geglu) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128));
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -360,6 +637,12 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   p.rows_per_vec = rows_per_vec > 0 ? rows_per_vec : 1;
   p.act = act;
   p.num_k_blocks = ceil_div(K, TC_BK);
+  if (use_persistent(geglu)) {
+    if (geglu) return launch_tc2<128, 6, false, true>(tmA, tmB, p, s);
+    if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 8, false, false>(tmA, tmB, p, s);
+    return launch_tc2<128, 6, false, false>(tmA, tmB, p, s);
+  }
   if (geglu) return launch_tc<128, false, true>(tmA, tmB, p, s);
   if (BN == 160) return launch_tc<160, false, false>(tmA, tmB, p, s);
   return launch_tc<128, false, false>(tmA, tmB, p, s);
@@ -383,7 +666,7 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   const int bw = Wo < 128 ? Wo : 128;
   const int bh = (128 / bw) < Ho ? (128 / bw) : Ho;
   const int bb = 128 / (bw * bh);
-  const int BN = (Cout % 160 == 0) ? 160 : 128;
+  const int BN = use_persistent() ? pick_bn(B * Ho * Wo, Cout) : ((Cout % 160 == 0) ? 160 : 128);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -408,6 +691,11 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   p.act = C2D_ACT_NONE;
   p.HW = Ho * Wo; p.W = Wo; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK); p.cstride = stride;
   p.num_k_blocks = 9 * p.cblocks;
+  if (use_persistent()) {
+    if (BN == 160) return launch_tc2<160, 5, true, false>(tmA, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 8, true, false>(tmA, tmB, p, s);
+    return launch_tc2<128, 6, true, false>(tmA, tmB, p, s);
+  }
   if (BN == 160) return launch_tc<160, true, false>(tmA, tmB, p, s);
   return launch_tc<128, true, false>(tmA, tmB, p, s);
 }
