@@ -10,10 +10,10 @@ int conv3x3_simt(const void*, const void*, const float*, const float*, const voi
                  int, int, cudaStream_t);
 bool linear_tc_supported(const void*, const void*, int, int, int, int);
 int linear_tc(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int, int,
-              int, bool, cudaStream_t);
+              int, bool, const GemmExtras*, cudaStream_t);
 bool conv3x3_tc_supported(const void*, const void*, int, int, int, int, int, int, int);
 int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int,
-               cudaStream_t);
+               long long*, cudaStream_t);
 int attention_simt(const AttnParams&, int, int, cudaStream_t);
 int attention_small(const AttnParams&, int, int, cudaStream_t);
 bool attention_tc_supported(const AttnParams&, int B);
@@ -37,10 +37,10 @@ int c2d_linear(const void* x, const void* w, const float* bias, const float* row
   bool tc_ok = dtype == C2D_BF16 && linear_tc_supported(x, w, M, N, K, ldx);
   if (impl == C2D_IMPL_TCGEN05) {
     C2D_REQUIRE(tc_ok, "linear: tcgen05 path needs bf16, K %% 8 == 0, ldx %% 8 == 0, aligned pointers");
-    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
+    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, nullptr, s);
   }
   if (impl == C2D_IMPL_AUTO && tc_ok && M >= 64)
-    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, s);
+    return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, nullptr, s);
   return linear_simt(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, dtype, s);
 }
 
@@ -51,7 +51,7 @@ int c2d_geglu_linear(const void* x, const void* w, const float* bias, void* y, i
   C2D_REQUIRE(dtype == C2D_BF16 && F % 64 == 0, "geglu_linear: fused path is bf16 with F %% 64 == 0");
   C2D_REQUIRE(linear_tc_supported(x, w, M, 2 * F, K, K), "geglu_linear: K %% 8 / alignment");
   (void)impl;
-  return linear_tc(x, w, bias, nullptr, 1, nullptr, y, M, 2 * F, K, K, F, 0, C2D_ACT_NONE, true, (cudaStream_t)stream);
+  return linear_tc(x, w, bias, nullptr, 1, nullptr, y, M, 2 * F, K, K, F, 0, C2D_ACT_NONE, true, nullptr, (cudaStream_t)stream);
 }
 
 int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y,
@@ -65,11 +65,44 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
   bool tc_ok = dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, upsample2x);
   if (impl == C2D_IMPL_TCGEN05) {
     C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, no fused upsample, pow2 output H/W, Cin %% 8 == 0, Cin >= 64");
-    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, s);
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, nullptr, s);
   }
   if (impl == C2D_IMPL_AUTO && tc_ok)
-    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, s);
+    return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, nullptr, s);
   return conv3x3_simt(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, upsample2x, dtype, s);
+}
+
+int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w, const float* bias, const float* rowvec,
+                  int rows_per_vec, const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act,
+                  long long* chan_stats, int stats_rows, int dtype, void* stream) {
+  C2D_REQUIRE(x && w && y, "linear_ex: null pointer");
+  C2D_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N, "linear_ex: bad dims M=%d N=%d K=%d ldy=%d", M, N, K, ldy);
+  C2D_REQUIRE(!residual || ldr >= N, "linear_ex: bad residual stride %d", ldr);
+  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_SILU, "linear_ex: bad act %d", act);
+  C2D_REQUIRE(dtype == C2D_BF16, "linear_ex: the K-concatenated / statistics-producing GEMM exists on the tcgen05 (bf16) path only");
+  C2D_REQUIRE(ldx >= (x2 ? K1 : K) && (!x2 || ldx2 >= K - K1), "linear_ex: bad row strides");
+  C2D_REQUIRE(linear_tc_supported(x, w, M, N, K, ldx), "linear_ex: K %% 8 / ldx %% 8 / alignment");
+  if (chan_stats) C2D_REQUIRE(stats_rows > 0 && M % stats_rows == 0, "linear_ex: M=%d is not a multiple of stats_rows=%d", M, stats_rows);
+  // the epilogue reduction needs whole warps (32 rows) inside one image; tiny planes take the stand-alone kernel
+  const bool fused = chan_stats && stats_rows % 32 == 0;
+  GemmExtras ex = {x2, K1, ldx2, fused ? chan_stats : nullptr, stats_rows};
+  int rc = linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, &ex, (cudaStream_t)stream);
+  if (rc || !chan_stats || fused) return rc;
+  C2D_REQUIRE(ldy == N, "linear_ex: channel statistics of a strided output need stats_rows %% 32 == 0");
+  return c2d_channel_stats(y, chan_stats, M / stats_rows, stats_rows, N, dtype, stream);
+}
+
+int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y,
+                   int B, int H, int W, int Cin, int Cout, int stride, long long* chan_stats, int dtype, void* stream) {
+  C2D_REQUIRE(x && w && y, "conv3x3_ex: null pointer");
+  C2D_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_ex: bad dims");
+  C2D_REQUIRE(dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
+              "conv3x3_ex: statistics-producing convolution exists on the tcgen05 (bf16) path only (H=%d W=%d Cin=%d)", H, W, Cin);
+  const int HWo = (H / stride) * (W / stride);
+  const bool fused = chan_stats && HWo % 32 == 0;
+  int rc = conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, fused ? chan_stats : nullptr, (cudaStream_t)stream);
+  if (rc || !chan_stats || fused) return rc;
+  return c2d_channel_stats(y, chan_stats, B, HWo, Cout, dtype, stream);
 }
 
 int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,

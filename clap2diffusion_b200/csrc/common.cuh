@@ -105,6 +105,14 @@ struct AttnParams {
   const uint8_t* mask;   // [B][Nkv] (1 = keep) or null
 };
 
+// optional inputs / outputs of the tcgen05 GEMM (see c2d_linear_ex)
+struct GemmExtras {
+  const void* x2;        // second A source: A = [x | x2] along K (first K1 columns from x)
+  int K1, ldx2;
+  long long* stats;      // per-channel fixed-point statistics of y: [M / stats_rows][N][2]
+  int stats_rows;
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int num_sms() {
   static int n = 0;

@@ -36,7 +36,47 @@ struct TcParams {
   int num_k_blocks;
   // conv geometry (HW, W: OUTPUT plane; cstride: convolution stride 1 | 2)
   int HW, W, Cin, cblocks, cstride;
+  // optional per-channel statistics of y for the consuming GroupNorm: stats[b][n][{sum, sumsq}] as 2^20 fixed-point
+  // 64-bit integers (integer atomics: the result does not depend on the order CTAs retire in); b = row / stats_rows
+  unsigned long long* stats;
+  int stats_rows;
+  // plain GEMM with A = [x | x2] concatenated along K: k-blocks >= kb_split come from the second tensor map
+  int kb_split;
 };
+
+constexpr float STATS_SCALE = 1048576.0f;      // 2^20
+
+// Epilogue helper.  Every lane holds sums (s) and sums of squares (q) of its 8 columns over the rows it drained;
+// lanes with equal (lane & 3) own the same columns.  A transposing butterfly (8 + 4 + 2 shuffles) leaves each of
+// the 8 lanes of a column group with 2 of its 16 totals, which go to the fixed-point accumulators.
+__device__ __forceinline__ void stats_commit(const float (&s)[8], const float (&q)[8], int lane, unsigned long long* dst,
+                                             int nvalid) {
+  float w[8], x[4], y[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = h16 ? s[i] : q[i];
+    const float keep = h16 ? q[i] : s[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h8 ? w[i] : w[4 + i];
+    const float keep = h8 ? w[4 + i] : w[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h4 ? x[i] : x[2 + i];
+    const float keep = h4 ? x[2 + i] : x[i];
+    y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const int col = (h8 ? 4 : 0) + (h4 ? 2 : 0), kind = h16 ? 1 : 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (col + i < nvalid)
+      atomicAdd(dst + (size_t)(col + i) * 2 + kind, (unsigned long long)__float2ll_rn(y[i] * STATS_SCALE));
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
@@ -93,7 +133,8 @@ struct TcCfg {
 
 template <int BN, bool CONV, bool GEGLU>
 __global__ void __launch_bounds__(TC_THREADS)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -143,7 +184,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
           tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
         } else {
-          tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+          if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+          else tma_load_2d(sA, &tmA2, &full[s], (kb - p.kb_split) * TC_BK, m0);
           tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
         }
       }
@@ -249,37 +291,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
     {
+      // coalesced drain, 32 columns at a time: lane = (row rsub of an 8-row block, 8-column group g); the four
+      // residual loads of a chunk are issued before any of them is consumed
       const int ncols = GEGLU ? (p.N >> 1) : p.N;            // logical output width
       const int nbase = GEGLU ? (n0 >> 1) : n0;
       const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
       const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
-      constexpr int GROUPS = NOUT / 8;                        // 8-column groups per row
-      constexpr int ITERS = GROUPS;                           // 32 rows * GROUPS groups / 32 lanes
-      constexpr int UNR = (ITERS % 5 == 0) ? 5 : 4;           // residual loads kept in flight per lane
-      static_assert(ITERS % UNR == 0, "epilogue unroll");
+      const int rsub = lane >> 2, g = lane & 3;
+      const int mrow0 = m0 + q * 32;
 #pragma unroll 1
-      for (int it0 = 0; it0 < ITERS; it0 += UNR) {
-        uint4 res[UNR];
-        bool ok[UNR];
+      for (int c = 0; c < NOUT / 32; ++c) {
+        const int n = nbase + c * 32 + g * 8;
+        const int nvalid = ncols - n;
+        uint4 res[4];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {                       // (1) all residual loads of the batch first
-          const int idx = lane + 32 * (it0 + u);
-          const int rr = idx / GROUPS, g = idx - rr * GROUPS;
-          const int m = m0 + q * 32 + rr, n = nbase + g * 8;
-          ok[u] = m < p.M && n < ncols;
+        for (int u = 0; u < 4; ++u) {
+          const int m = mrow0 + u * 8 + rsub;
           res[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u] && vec_r && ncols - n >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
+          if (m < p.M && vec_r && nvalid >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
         }
+        float ssum[8], ssq[8];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {                       // (2) drain
-          if (!ok[u]) continue;
-          const int idx = lane + 32 * (it0 + u);
-          const int rr = idx / GROUPS, g = idx - rr * GROUPS;
-          const int m = m0 + q * 32 + rr, n = nbase + g * 8;
-          const float* sp = stage + (size_t)rr * PITCH + g * 8;
+        for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = u * 8 + rsub, m = mrow0 + rr;
+          if (m >= p.M || nvalid <= 0) continue;
+          const float* sp = stage + (size_t)rr * PITCH + c * 32 + g * 8;
           const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
           float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-          const int nvalid = ncols - n;
           bf16* yp = p.y + (long long)m * p.ldy + n;
           if (p.residual) {
             if (vec_r && nvalid >= 8) {
@@ -298,6 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(v[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+        }
+        if (p.stats) {      // uniform across the CTA; rows of one warp lie in one image (stats_rows % 32 == 0)
+          const int bimg = mrow0 / p.stats_rows;
+          stats_commit(ssum, ssq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
         }
       }
     }
@@ -311,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, bool CONV, bool GEGLU>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -324,7 +370,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
     attr_done = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM));
-  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -352,8 +398,8 @@ struct Tc2Cfg {
 
 template <int BN, int STAGES, bool CONV, bool GEGLU>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-                const int num_tiles, const int num_n) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
   using Cfg = Tc2Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -405,7 +451,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
             tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
           } else {
-            tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+            if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+            else tma_load_2d(sA, &tmA2, &full[s], (kb - p.kb_split) * TC_BK, m0);
             tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
           }
         }
@@ -510,24 +557,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         // ---- coalesced drain: 32 rows x 4 groups of 8 columns; residual loads of all 4 items issued first
         uint4 res[4];
-        bool ok[4];
+        const int rsub = lane >> 2, g = lane & 3;
+        const int mrow0 = m0 + q * 32;
+        const int n = nbase + c * 32 + g * 8;
+        const int nvalid = ncols - n;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int rr = u * 8 + (lane >> 2), g = lane & 3;
-          const int m = m0 + q * 32 + rr, n = nbase + c * 32 + g * 8;
-          ok[u] = m < p.M && n < ncols;
+          const int m = mrow0 + u * 8 + rsub;
           res[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u] && vec_r && ncols - n >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
+          if (m < p.M && vec_r && nvalid >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
         }
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          const int rr = u * 8 + (lane >> 2), g = lane & 3;
-          const int m = m0 + q * 32 + rr, n = nbase + c * 32 + g * 8;
+          const int rr = u * 8 + rsub, m = mrow0 + rr;
+          if (m >= p.M || nvalid <= 0) continue;
           const float* sp = stage + (size_t)rr * Cfg::EPI_PITCH + g * 8;
           const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
           float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-          const int nvalid = ncols - n;
           bf16* yp = p.y + (long long)m * p.ldy + n;
           if (p.residual) {
             if (vec_r && nvalid >= 8) {
@@ -546,6 +595,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+        }
+        if (p.stats) {
+          const int bimg = mrow0 / p.stats_rows;
+          stats_commit(ssum, ssq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
         }
         __syncwarp();
       }
@@ -560,7 +615,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int BN, int STAGES, bool CONV, bool GEGLU>
-static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = Tc2Cfg<BN, STAGES>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "persistent GEMM smem");
   static bool attr_done = false;
@@ -576,7 +631,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPa
   const int num_n = ceil_div(p.N, BN);
   const int num_tiles = num_n * ceil_div(p.M, TC_BM);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p, num_tiles, num_n);
+  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_tiles, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -612,17 +667,34 @@ bool linear_tc_supported(const void* x, const void* w, int M, int N, int K, int 
 
 int linear_tc(const void* x, const void* w, const float* bias, const float* rowvec, int rows_per_vec,
               const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act, bool geglu,
-              cudaStream_t s) {
+              const GemmExtras* ex, cudaStream_t s) {
   C2D_REQUIRE(linear_tc_supported(x, w, M, N, K, ldx),
               "linear_tc: needs bf16, K %% 8 == 0, ldx %% 8 == 0, 16B-aligned x/w (M=%d N=%d K=%d ldx=%d)", M, N, K, ldx);
+  const bool cat = ex && ex->x2;
+  const int K1 = cat ? ex->K1 : K;
+  if (cat)
+    C2D_REQUIRE(K1 > 0 && K1 < K && K1 % TC_BK == 0 && ex->ldx2 % 8 == 0 && al16(ex->x2),
+                "linear_tc: K-concatenated input needs K1 %% 64 == 0 (K1=%d K=%d ldx2=%d)", K1, K, ex->ldx2);
+  if (ex && ex->stats)
+    C2D_REQUIRE(!geglu && ex->stats_rows > 0 && ex->stats_rows % 32 == 0 && M % ex->stats_rows == 0,
+                "linear_tc: channel statistics need rows-per-image %% 32 == 0 (M=%d stats_rows=%d)", M, ex->stats_rows);
   const int BN = geglu ? 128 : (use_persistent(geglu) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128));
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmA2, tmB;
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
     uint64_t st[1] = {(uint64_t)ldx * 2};
     uint32_t box[2] = {TC_BK, TC_BM};
     int rc = make_tmap_bf16(&tmA, x, 2, dims, st, box);
     if (rc) return rc;
+  }
+  if (cat) {
+    uint64_t dims[2] = {(uint64_t)(K - K1), (uint64_t)M};
+    uint64_t st[1] = {(uint64_t)ex->ldx2 * 2};
+    uint32_t box[2] = {TC_BK, TC_BM};
+    int rc = make_tmap_bf16(&tmA2, ex->x2, 2, dims, st, box);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
@@ -637,15 +709,18 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   p.rows_per_vec = rows_per_vec > 0 ? rows_per_vec : 1;
   p.act = act;
   p.num_k_blocks = ceil_div(K, TC_BK);
+  p.kb_split = cat ? K1 / TC_BK : p.num_k_blocks;
+  p.stats = ex ? reinterpret_cast<unsigned long long*>(ex->stats) : nullptr;
+  p.stats_rows = ex && ex->stats ? ex->stats_rows : 1;
   if (use_persistent(geglu)) {
-    if (geglu) return launch_tc2<128, 6, false, true>(tmA, tmB, p, s);
-    if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmB, p, s);
-    if (BN == 64) return launch_tc2<64, 8, false, false>(tmA, tmB, p, s);
-    return launch_tc2<128, 6, false, false>(tmA, tmB, p, s);
+    if (geglu) return launch_tc2<128, 6, false, true>(tmA, tmA2, tmB, p, s);
+    if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmA2, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 8, false, false>(tmA, tmA2, tmB, p, s);
+    return launch_tc2<128, 6, false, false>(tmA, tmA2, tmB, p, s);
   }
-  if (geglu) return launch_tc<128, false, true>(tmA, tmB, p, s);
-  if (BN == 160) return launch_tc<160, false, false>(tmA, tmB, p, s);
-  return launch_tc<128, false, false>(tmA, tmB, p, s);
+  if (geglu) return launch_tc<128, false, true>(tmA, tmA2, tmB, p, s);
+  if (BN == 160) return launch_tc<160, false, false>(tmA, tmA2, tmB, p, s);
+  return launch_tc<128, false, false>(tmA, tmA2, tmB, p, s);
 }
 
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -659,7 +734,7 @@ bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int
 }
 
 int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
-               int H, int W, int Cin, int Cout, int stride, cudaStream_t s) {
+               int H, int W, int Cin, int Cout, int stride, long long* stats, cudaStream_t s) {
   C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
               "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0, Cin >= 64 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
   const int Ho = H / stride, Wo = W / stride;
@@ -691,13 +766,17 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   p.act = C2D_ACT_NONE;
   p.HW = Ho * Wo; p.W = Wo; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK); p.cstride = stride;
   p.num_k_blocks = 9 * p.cblocks;
+  p.kb_split = p.num_k_blocks;
+  if (stats) C2D_REQUIRE((Ho * Wo) % 32 == 0, "conv3x3_tc: channel statistics need Ho*Wo %% 32 == 0 (%d)", Ho * Wo);
+  p.stats = reinterpret_cast<unsigned long long*>(stats);
+  p.stats_rows = Ho * Wo;
   if (use_persistent()) {
-    if (BN == 160) return launch_tc2<160, 5, true, false>(tmA, tmB, p, s);
-    if (BN == 64) return launch_tc2<64, 8, true, false>(tmA, tmB, p, s);
-    return launch_tc2<128, 6, true, false>(tmA, tmB, p, s);
+    if (BN == 160) return launch_tc2<160, 5, true, false>(tmA, tmA, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 8, true, false>(tmA, tmA, tmB, p, s);
+    return launch_tc2<128, 6, true, false>(tmA, tmA, tmB, p, s);
   }
-  if (BN == 160) return launch_tc<160, true, false>(tmA, tmB, p, s);
-  return launch_tc<128, true, false>(tmA, tmB, p, s);
+  if (BN == 160) return launch_tc<160, true, false>(tmA, tmA, tmB, p, s);
+  return launch_tc<128, true, false>(tmA, tmA, tmB, p, s);
 }
 
 int init_tc(int device) {

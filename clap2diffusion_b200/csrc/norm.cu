@@ -20,7 +20,13 @@ __device__ __forceinline__ void gn_load(const T* __restrict__ x, const T* __rest
 // SiLU: accurate in the fp32 parity mode; MUFU ex2 + rcp in bf16 mode (the result is rounded to bf16 anyway)
 template <typename T> __device__ __forceinline__ float gn_silu(float v);
 template <> __device__ __forceinline__ float gn_silu<float>(float v) { return silu_acc(v); }
-template <> __device__ __forceinline__ float gn_silu<bf16>(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU.TANH (rel. error ~2^-11, below the bf16 rounding of the result)
+template <> __device__ __forceinline__ float gn_silu<bf16>(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // grid: (slabs, B).  Each CTA reduces `rows_per_cta` rows of one image into stats[b][g][{sum,sumsq}].
 template <typename T>
@@ -173,6 +179,165 @@ gn_apply_kernel(const T* __restrict__ x, const T* __restrict__ x2, const float* 
   }
 }
 
+// =====================================================================================================
+// GroupNorm from producer-side channel statistics (bf16 product path).
+//   chan stats: long long [B][C][2] = 2^20 fixed-point (sum, sum of squares) per channel, accumulated with integer
+//   atomics by the producing GEMM / conv epilogue (gemm_tc.cu: stats_commit) or by chan_stats_kernel below --
+//   integer adds commute, so the statistics (and therefore the whole denoising trajectory) are bit-reproducible.
+//   The apply kernel is ONE pass: read x (and the skip tensor x2), write y.  Algorithmic traffic 4 B / element.
+// =====================================================================================================
+constexpr int GN2_MAX_THREADS = 512;
+constexpr int GN2_UNROLL = 4;
+constexpr double STATS_INV_SCALE = 1.0 / 1048576.0;
+
+template <typename T>
+__global__ void __launch_bounds__(GN2_MAX_THREADS, 2)
+gn_apply2_kernel(const T* __restrict__ x, const T* __restrict__ x2, const long long* __restrict__ st1,
+                 const long long* __restrict__ st2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 T* __restrict__ y, int HW, int C1, int C2, int groups, float eps, int silu, int rows_per_cta) {
+  const int C = C1 + C2, nvec = C >> 3, cpg = C / groups;
+  const int b = blockIdx.y;
+  const int rif = blockDim.x / nvec;                    // rows in flight (blockDim is a multiple of nvec)
+  const int my_vec = threadIdx.x % nvec, my_rl = threadIdx.x / nvec;
+  const int c0 = my_vec * 8;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  const T* src;
+  long long rowstride;
+  if (c0 < C1) { src = x + (long long)b * HW * C1 + c0; rowstride = C1; }
+  else { src = x2 + (long long)b * HW * C2 + (c0 - C1); rowstride = C2; }
+  T* dst = y + (long long)b * HW * C + c0;
+
+  // first batch of loads goes out before the statistics are touched
+  int r = r0 + my_rl;
+  uint4 pre[GN2_UNROLL];
+  static_assert(sizeof(T) == 2, "gn_apply2 is the bf16 path");
+#pragma unroll
+  for (int u = 0; u < GN2_UNROLL; ++u) {
+    const int rr = r + u * rif;
+    pre[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (rr < r1) pre[u] = *reinterpret_cast<const uint4*>(src + (long long)rr * rowstride);
+  }
+
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  {
+    // one warp per group (round robin): lanes stride over the group's channels, fixed-order butterfly in double
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < groups; g += nwarps) {
+      long long a = 0, q = 0;
+      for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+        const long long* sp = c < C1 ? st1 + ((long long)b * C1 + c) * 2 : st2 + ((long long)b * C2 + (c - C1)) * 2;
+        a += sp[0];
+        q += sp[1];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        const double inv_n = 1.0 / ((double)HW * (double)cpg);
+        const double mean = (double)a * STATS_INV_SCALE * inv_n;
+        double var = (double)q * STATS_INV_SCALE * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)mean;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
+  }
+  __syncthreads();
+  float a[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j, g = c / cpg;
+    a[j] = s_rstd[g] * __ldg(gamma + c);
+    sh[j] = __ldg(beta + c) - s_mean[g] * a[j];
+  }
+  auto emit = [&](const uint4& raw, int rr) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = fmaf(f[j], a[j], sh[j]);
+      f[j] = silu ? gn_silu<T>(v) : v;
+    }
+    Vec8<T>::store(dst + (long long)rr * C, f);
+  };
+  for (;;) {
+#pragma unroll
+    for (int u = 0; u < GN2_UNROLL; ++u) {
+      const int rr = r + u * rif;
+      if (rr < r1) emit(pre[u], rr);
+    }
+    r += GN2_UNROLL * rif;
+    if (r >= r1) break;
+#pragma unroll
+    for (int u = 0; u < GN2_UNROLL; ++u) {
+      const int rr = r + u * rif;
+      if (rr < r1) pre[u] = *reinterpret_cast<const uint4*>(src + (long long)rr * rowstride);
+    }
+  }
+}
+
+// Stand-alone producer of the same statistics for tensors that do not come out of a tcgen05 epilogue (conv_in).
+template <typename T>
+__global__ void __launch_bounds__(GN2_MAX_THREADS, 2)
+chan_stats_kernel(const T* __restrict__ x, unsigned long long* __restrict__ stats, int HW, int C, int rows_per_cta) {
+  const int nvec = C >> 3;
+  const int b = blockIdx.y;
+  const int rif = blockDim.x / nvec;
+  const int my_vec = threadIdx.x % nvec, my_rl = threadIdx.x / nvec;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  const T* src = x + (long long)b * HW * C + my_vec * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (int r = r0 + my_rl; r < r1; r += GN2_UNROLL * rif) {
+    float f[GN2_UNROLL][8];
+#pragma unroll
+    for (int u = 0; u < GN2_UNROLL; ++u) {
+      const int rr = r + u * rif;
+      if (rr < r1) Vec8<T>::load(src + (long long)rr * C, f[u]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GN2_UNROLL; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[u][j]; q[j] = fmaf(f[u][j], f[u][j], q[j]); }
+  }
+  // fixed-order fold over the row lanes through smem, then one integer atomic per (channel, moment)
+  extern __shared__ float s_part[];            // [rif][C][2]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_part[((size_t)my_rl * C + my_vec * 8 + j) * 2 + 0] = s[j];
+    s_part[((size_t)my_rl * C + my_vec * 8 + j) * 2 + 1] = q[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int rl = 0; rl < rif; ++rl) t += s_part[(size_t)rl * C * 2 + i];
+    atomicAdd(stats + (size_t)b * C * 2 + i, (unsigned long long)__float2ll_rn(t * 1048576.0f));
+  }
+}
+
+static int gn2_threads(int C) {
+  const int nvec = C / 8;
+  return (GN2_MAX_THREADS / nvec) * nvec;
+}
+static void gn2_grid(int B, int HW, int rif, dim3* grid, int* rows_per_cta) {
+  int slabs = (2 * num_sms()) / B;               // at most one full wave of 2 CTAs per SM
+  if (slabs < 1) slabs = 1;
+  int rpc = ceil_div(HW, slabs);
+  rpc = ceil_div(rpc, rif) * rif;               // whole row batches per CTA
+  if (rpc < rif) rpc = rif;
+  *rows_per_cta = rpc;
+  *grid = dim3(ceil_div(HW, rpc), B);
+}
+
 // ---- LayerNorm: one warp handles ROWS rows at once (ROWS x ITERS independent 128-bit loads in flight per lane),
 // rows kept in registers, two-pass statistics in registers.  C % 8 == 0 and C <= 256 * ITERS.
 template <typename T, int ITERS, int ROWS>
@@ -295,6 +460,38 @@ int c2d_group_norm(const void* x, const void* x2, const float* gamma, const floa
     set_error("group_norm: bad dtype %d", dtype);
     return C2D_ERR_ARG;
   }
+  return check_launch("gn_apply");
+}
+
+int c2d_channel_stats(const void* x, long long* chan_stats, int B, int HW, int C, int dtype, void* stream) {
+  C2D_REQUIRE(x && chan_stats && B > 0 && HW > 0 && C > 0, "channel_stats: bad args");
+  C2D_REQUIRE(dtype == C2D_BF16, "channel_stats: bf16 product path only (fp32 mode uses c2d_group_norm)");
+  C2D_REQUIRE(C % 8 == 0 && C / 8 <= GN2_MAX_THREADS, "channel_stats: C=%d must be a multiple of 8 and <= %d", C, 8 * GN2_MAX_THREADS);
+  const int threads = gn2_threads(C), rif = threads / (C / 8);
+  dim3 grid;
+  int rpc;
+  gn2_grid(B, HW, rif, &grid, &rpc);
+  const size_t smem = sizeof(float) * 2 * (size_t)rif * C;
+  C2D_REQUIRE(smem <= 48 * 1024, "channel_stats: C=%d needs %zu B of shared memory", C, smem);
+  chan_stats_kernel<bf16><<<grid, threads, smem, (cudaStream_t)stream>>>((const bf16*)x, (unsigned long long*)chan_stats, HW, C, rpc);
+  return check_launch("chan_stats");
+}
+
+int c2d_group_norm_apply(const void* x, const void* x2, const long long* stats1, const long long* stats2, const float* gamma,
+                         const float* beta, void* y, int B, int HW, int C1, int C2, int groups, float eps, int silu,
+                         int dtype, void* stream) {
+  C2D_REQUIRE(x && stats1 && gamma && beta && y, "group_norm_apply: null pointer");
+  C2D_REQUIRE(B > 0 && HW > 0 && C1 > 0 && C2 >= 0 && (C2 == 0 || (x2 && stats2)), "group_norm_apply: bad dims / missing second source");
+  C2D_REQUIRE(dtype == C2D_BF16, "group_norm_apply: bf16 product path only (fp32 mode uses c2d_group_norm)");
+  const int C = C1 + C2;
+  C2D_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN2_MAX_THREADS, "group_norm_apply: C1=%d C2=%d", C1, C2);
+  C2D_REQUIRE(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "group_norm_apply: bad groups %d for C=%d", groups, C);
+  const int threads = gn2_threads(C), rif = threads / (C / 8);
+  dim3 grid;
+  int rpc;
+  gn2_grid(B, HW, rif, &grid, &rpc);
+  gn_apply2_kernel<bf16><<<grid, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)x2, stats1, stats2, gamma, beta,
+                                                                      (bf16*)y, HW, C1, C2, groups, eps, silu, rpc);
   return check_launch("gn_apply");
 }
 

@@ -107,10 +107,17 @@ def _rows(x: torch.Tensor):
 
 # ------------------------------------------------------------------------------------------------
 def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_per_vec=1, out=None,
-           impl=IMPL_AUTO):
-    """y = act(x @ w.T + bias + rowvec[row // rows_per_vec]) + residual.   w: [N, K] (nn.Linear layout)."""
+           impl=IMPL_AUTO, x2=None, stats=None, stats_rows=0):
+    """y = act([x | x2] @ w.T + bias + rowvec[row // rows_per_vec]) + residual.   w: [N, K] (nn.Linear layout).
+    x2: optional second source concatenated along K (bf16 tcgen05 path).  stats: optional int64 [B, N, 2] channel
+    statistics accumulator (rows_per_image = stats_rows) filled by the epilogue for group_norm_apply."""
     _dev(x)
-    M, K, ldx = _rows(x)
+    M, K1, ldx = _rows(x)
+    K, ldx2 = K1, 0
+    if x2 is not None:
+        M2, K2, ldx2 = _rows(x2)
+        assert M2 == M and x2.dtype == x.dtype
+        K = K1 + K2
     N = w.shape[0]
     assert w.shape[1] == K and w.is_contiguous() and w.dtype == x.dtype, (w.shape, K, w.dtype, x.dtype)
     if out is None:
@@ -122,9 +129,16 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_pe
         Mr, Nr, ldr = _rows(residual)
         assert Mr == M and Nr == N and residual.dtype == x.dtype
     with _Timed(2.0 * M * N * K, _nb(w, residual) + (M * K + M * N) * x.element_size()):
-        check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
-                             int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
-                             impl, _stream()), "linear")
+        if x2 is None and stats is None:
+            check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                                 int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
+                                 impl, _stream()), "linear")
+        else:
+            if stats is not None:
+                assert stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == (M // stats_rows) * N * 2
+            check(lib.c2d_linear_ex(x.data_ptr(), _ptr(x2), K1, ldx2, w.data_ptr(), _ptr(_f32(bias, "bias")),
+                                    _ptr(_f32(rowvec, "rowvec")), int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K,
+                                    ldx, ldy, ldr, act, _ptr(stats), int(stats_rows), _dt(x), _stream()), "linear_ex")
     return out
 
 
@@ -143,8 +157,9 @@ def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=IMPL_AUTO):
 
 
 def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, upsample=False, out=None,
-            impl=IMPL_AUTO):
-    """x [B,H,W,Cin] NHWC; w_packed [Cout,3,3,Cin]; returns [B,Ho,Wo,Cout]."""
+            impl=IMPL_AUTO, stats=None):
+    """x [B,H,W,Cin] NHWC; w_packed [Cout,3,3,Cin]; returns [B,Ho,Wo,Cout].  stats: optional int64 [B,Cout,2]
+    channel-statistics accumulator filled by the epilogue (bf16 tcgen05 path)."""
     _dev(x)
     B, H, W, Cin = x.shape
     Cout = w_packed.shape[0]
@@ -157,9 +172,15 @@ def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, ups
     if residual is not None:
         assert residual.is_contiguous() and residual.numel() == out.numel() and residual.dtype == x.dtype
     with _Timed(2.0 * B * Ho * Wo * Cout * 9 * Cin, _nb(x, w_packed, out, residual)):
-        check(lib.c2d_conv3x3(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
-                              _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout, stride, int(bool(upsample)), _dt(x),
-                              impl, _stream()), "conv3x3")
+        if stats is None:
+            check(lib.c2d_conv3x3(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
+                                  _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout, stride, int(bool(upsample)), _dt(x),
+                                  impl, _stream()), "conv3x3")
+        else:
+            assert not upsample and stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == B * Cout * 2
+            check(lib.c2d_conv3x3_ex(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")),
+                                     _ptr(_f32(rowvec, "rowvec")), _ptr(residual), out.data_ptr(), B, H, W, Cin, Cout,
+                                     stride, stats.data_ptr(), _dt(x), _stream()), "conv3x3_ex")
     return out
 
 
@@ -188,6 +209,36 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_
         check(lib.c2d_group_norm(x.data_ptr(), _ptr(x2), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
                                  out.data_ptr(), _ptr(raw_cat), ws.data_ptr(), B, N, C1, C2, groups, float(eps),
                                  int(bool(silu)), _dt(x), _stream()), "group_norm")
+    return out
+
+
+def channel_stats(x, stats):
+    """Accumulate per-channel (sum, sumsq) of x [B,N,C] into the int64 [B,C,2] fixed-point accumulator `stats`."""
+    _dev(x)
+    B, C = x.shape[0], x.shape[-1]
+    N = x.numel() // (B * C)
+    assert x.is_contiguous() and stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == B * C * 2
+    with _Timed(0.0, _nb(x)):
+        check(lib.c2d_channel_stats(x.data_ptr(), stats.data_ptr(), B, N, C, _dt(x), _stream()), "channel_stats")
+    return stats
+
+
+def group_norm_apply(x, stats, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, stats2=None, out=None):
+    """GroupNorm(+SiLU) of cat([x, x2], -1) from producer-side channel statistics: one pass, no statistics read."""
+    _dev(x)
+    B, C1 = x.shape[0], x.shape[-1]
+    N = x.numel() // (B * C1)
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x.dtype and stats2 is not None))
+    assert stats.dtype == torch.int64 and stats.numel() == B * C1 * 2
+    assert stats2 is None or (stats2.dtype == torch.int64 and stats2.numel() == B * C2 * 2)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], C1 + C2, device=x.device, dtype=x.dtype)
+    with _Timed(0.0, _nb(x, x2, out)):
+        check(lib.c2d_group_norm_apply(x.data_ptr(), _ptr(x2), stats.data_ptr(), _ptr(stats2),
+                                       _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(), out.data_ptr(),
+                                       B, N, C1, C2, groups, float(eps), int(bool(silu)), _dt(x), _stream()),
+              "group_norm_apply")
     return out
 
 

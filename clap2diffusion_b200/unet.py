@@ -10,6 +10,9 @@ Design points (B200-first, not a port of diffusers):
     outputs for all timesteps (``time_table``), the audio injection and the attn2 K/V projections
     (``prepare_conditioning``);
   * attn1 uses one fused QKV GEMM; GEGLU is fused into the FF GEMM epilogue (bf16 mode);
+  * bf16 mode: every tensor a GroupNorm will read leaves its producer's epilogue together with per-channel
+    fixed-point statistics (``ops.linear/conv3x3(stats=...)``), so GroupNorm is ONE pass (``group_norm_apply``), and
+    the shortcut GEMM reads [h | skip] through two tensor maps instead of a materialised concat;
   * the launch sequence has no host synchronisation, so a whole step is capturable in a CUDA graph.
 
 The module exposes ``attn_processors`` / ``set_attn_processor`` with diffusers' processor names so the
@@ -107,6 +110,22 @@ def unet_topology():
     return down, up
 
 
+class _StatsArena:
+    """Zero-initialised int64 arena for the per-tensor channel statistics of one forward pass ([B, C, 2] each)."""
+
+    def __init__(self, device, capacity: int):
+        self.buf = torch.zeros(capacity, device=device, dtype=torch.int64)
+        self.off = 0
+
+    def take(self, B: int, C: int) -> torch.Tensor:
+        n = B * C * 2
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("channel-statistics arena exhausted")
+        v = self.buf[self.off:self.off + n]
+        self.off += n
+        return v
+
+
 class SD15UNet:
     """``SD15UNet(state_dict, device, dtype)``; state-dict keys/shapes are diffusers' (fp32, any device)."""
 
@@ -116,6 +135,8 @@ class SD15UNet:
         self.dtype = dtype
         self.impl = impl
         self.fuse_geglu = dtype == torch.bfloat16
+        self.fused_gn = dtype == torch.bfloat16       # producer-side GroupNorm statistics (tcgen05 epilogues)
+        self._gn_channels = 0
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
         self.sites: Dict[str, AttentionSite] = {}
@@ -150,6 +171,8 @@ class SD15UNet:
     def _norm(self, prefix):
         self.w[f"{prefix}.weight"] = self._dev32(f"{prefix}.weight")
         self.w[f"{prefix}.bias"] = self._dev32(f"{prefix}.bias")
+        if "transformer_blocks" not in prefix:             # GroupNorm site: bounds the statistics arena
+            self._gn_channels += self.w[f"{prefix}.weight"].numel()
 
     def _pack_resnet(self, name, cin, cout):
         self._norm(f"{name}.norm1"); self._conv(f"{name}.conv1")
@@ -284,34 +307,51 @@ class SD15UNet:
         return out
 
     # ------------------------------------------------------------------ forward
-    def _resnet(self, name, x, temb_row, skip=None):
+    def _resnet(self, name, x, temb_row, skip=None, xs=None, skip_s=None, ar=None):
+        """ResnetBlock2D.  bf16 mode: (x, xs) / (skip, skip_s) are tensors with their channel statistics and the
+        block returns (out, out_stats); fp32 mode: statistics are None and GroupNorm is the two-pass kernel."""
         w = self.w
         B = x.shape[0]
         cin = x.shape[-1] + (0 if skip is None else skip.shape[-1])
         cout = w[f"{name}.conv1.weight"].shape[0]
         has_sc = f"{name}.conv_shortcut.weight" in w
+        off = self._temb_offsets[name]
+        if skip is not None and not has_sc:
+            raise RuntimeError("concat resnet without shortcut is not part of SD-1.5")
+        if ar is not None:
+            h = ops.group_norm_apply(x, xs, w[f"{name}.norm1.weight"], w[f"{name}.norm1.bias"], GROUPS, 1e-5, True,
+                                     x2=skip, stats2=skip_s)
+            s1 = ar.take(B, cout)
+            h = ops.conv3x3(h, w[f"{name}.conv1.weight"], temb_row[off:off + cout], impl=self.impl, stats=s1)
+            h = ops.group_norm_apply(h, s1, w[f"{name}.norm2.weight"], w[f"{name}.norm2.bias"], GROUPS, 1e-5, True)
+            sc = x
+            if has_sc:
+                sc = ops.linear(x, w[f"{name}.conv_shortcut.weight"], w[f"{name}.conv_shortcut.bias"], x2=skip, impl=self.impl)
+            so = ar.take(B, cout)
+            out = ops.conv3x3(h, w[f"{name}.conv2.weight"], w[f"{name}.conv2.bias"], residual=sc, impl=self.impl, stats=so)
+            return out, so
         raw = None
         if skip is not None and has_sc:
             raw = torch.empty(*x.shape[:-1], cin, device=x.device, dtype=x.dtype)
         h = ops.group_norm(x, w[f"{name}.norm1.weight"], w[f"{name}.norm1.bias"], GROUPS, 1e-5, True, x2=skip, raw_cat=raw)
-        off = self._temb_offsets[name]
         h = ops.conv3x3(h, w[f"{name}.conv1.weight"], temb_row[off:off + cout], impl=self.impl)   # bias+temb row
         h = ops.group_norm(h, w[f"{name}.norm2.weight"], w[f"{name}.norm2.bias"], GROUPS, 1e-5, True)
         if has_sc:
             src = raw if raw is not None else x
             sc = ops.linear(src, w[f"{name}.conv_shortcut.weight"], w[f"{name}.conv_shortcut.bias"], impl=self.impl)
         else:
-            if skip is not None:
-                raise RuntimeError("concat resnet without shortcut is not part of SD-1.5")
             sc = x
-        return ops.conv3x3(h, w[f"{name}.conv2.weight"], w[f"{name}.conv2.bias"], residual=sc, impl=self.impl)
+        return ops.conv3x3(h, w[f"{name}.conv2.weight"], w[f"{name}.conv2.bias"], residual=sc, impl=self.impl), None
 
-    def _transformer(self, name, x, kv, ehs, kw):
+    def _transformer(self, name, x, kv, ehs, kw, xs=None, ar=None):
         w = self.w
         B, H, W, C = x.shape
         tb = f"{name}.transformer_blocks.0"
         res = x.view(B, H * W, C)
-        h = ops.group_norm(res, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], GROUPS, 1e-6, False)
+        if ar is not None:
+            h = ops.group_norm_apply(res, xs, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], GROUPS, 1e-6, False)
+        else:
+            h = ops.group_norm(res, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], GROUPS, 1e-6, False)
         h = ops.linear(h, w[f"{name}.proj_in.weight"], w[f"{name}.proj_in.bias"], impl=self.impl)
         # attn1
         s1 = self.sites[f"{tb}.attn1"]
@@ -335,8 +375,10 @@ class SD15UNet:
         else:
             g = ops.geglu(ops.linear(n3, w[f"{tb}.ff.net.0.proj.weight"], w[f"{tb}.ff.net.0.proj.bias"], impl=self.impl))
         h = ops.linear(g, w[f"{tb}.ff.net.2.weight"], w[f"{tb}.ff.net.2.bias"], residual=h, impl=self.impl)
-        out = ops.linear(h, w[f"{name}.proj_out.weight"], w[f"{name}.proj_out.bias"], residual=res, impl=self.impl)
-        return out.view(B, H, W, C)
+        so = ar.take(B, C) if ar is not None else None
+        out = ops.linear(h, w[f"{name}.proj_out.weight"], w[f"{name}.proj_out.bias"], residual=res, impl=self.impl,
+                         stats=so, stats_rows=H * W)
+        return out.view(B, H, W, C), so
 
     def forward_nhwc(self, x: torch.Tensor, temb_row: torch.Tensor, kv: Optional[Dict[str, torch.Tensor]] = None,
                      encoder_hidden_states: Optional[torch.Tensor] = None,
@@ -344,38 +386,47 @@ class SD15UNet:
         """x [B,H,W,4] (engine dtype), temb_row fp32 [sum(Cout)] (one row of time_table) -> eps [B,H,W,4]."""
         w, kw = self.w, (cross_attention_kwargs or {})
         ehs = encoder_hidden_states
+        B = x.shape[0]
+        ar = _StatsArena(x.device, 2 * B * self._gn_channels) if self.fused_gn else None
         h = ops.conv3x3(x, w["conv_in.weight"], w["conv_in.bias"], impl=self.impl)
+        hs = ops.channel_stats(h, ar.take(B, h.shape[-1])) if ar is not None else None
         if taps is not None:
             taps["conv_in"] = h
-        skips = [h]
+        skips = [(h, hs)]
         for i, blk in enumerate(self.down):
             for j in range(2):
-                h = self._resnet(f"down_blocks.{i}.resnets.{j}", h, temb_row)
+                h, hs = self._resnet(f"down_blocks.{i}.resnets.{j}", h, temb_row, xs=hs, ar=ar)
                 if blk["attn"]:
-                    h = self._transformer(f"down_blocks.{i}.attentions.{j}", h, kv, ehs, kw)
-                skips.append(h)
+                    h, hs = self._transformer(f"down_blocks.{i}.attentions.{j}", h, kv, ehs, kw, xs=hs, ar=ar)
+                skips.append((h, hs))
             if blk["sample"]:
                 n = f"down_blocks.{i}.downsamplers.0.conv"
-                h = ops.conv3x3(h, w[f"{n}.weight"], w[f"{n}.bias"], stride=2, impl=self.impl)
-                skips.append(h)
-        h = self._resnet("mid_block.resnets.0", h, temb_row)
-        h = self._transformer("mid_block.attentions.0", h, kv, ehs, kw)
-        h = self._resnet("mid_block.resnets.1", h, temb_row)
+                hs = ar.take(B, w[f"{n}.weight"].shape[0]) if ar is not None else None
+                h = ops.conv3x3(h, w[f"{n}.weight"], w[f"{n}.bias"], stride=2, impl=self.impl, stats=hs)
+                skips.append((h, hs))
+        h, hs = self._resnet("mid_block.resnets.0", h, temb_row, xs=hs, ar=ar)
+        h, hs = self._transformer("mid_block.attentions.0", h, kv, ehs, kw, xs=hs, ar=ar)
+        h, hs = self._resnet("mid_block.resnets.1", h, temb_row, xs=hs, ar=ar)
         if taps is not None:
             taps["mid"] = h
         for i, blk in enumerate(self.up):
             for j in range(3):
-                h = self._resnet(f"up_blocks.{i}.resnets.{j}", h, temb_row, skip=skips.pop())
+                sk, sks = skips.pop()
+                h, hs = self._resnet(f"up_blocks.{i}.resnets.{j}", h, temb_row, skip=sk, xs=hs, skip_s=sks, ar=ar)
                 if blk["attn"]:
-                    h = self._transformer(f"up_blocks.{i}.attentions.{j}", h, kv, ehs, kw)
+                    h, hs = self._transformer(f"up_blocks.{i}.attentions.{j}", h, kv, ehs, kw, xs=hs, ar=ar)
             if blk["sample"]:
                 n = f"up_blocks.{i}.upsamplers.0.conv"
-                if self.dtype == torch.bfloat16:
-                    h = ops.conv3x3(ops.upsample2x(h), w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl)
+                if self.dtype == torch.bfloat16 or ar is not None:
+                    hs = ar.take(B, w[f"{n}.weight"].shape[0]) if ar is not None else None
+                    h = ops.conv3x3(ops.upsample2x(h), w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl, stats=hs)
                 else:
                     h = ops.conv3x3(h, w[f"{n}.weight"], w[f"{n}.bias"], upsample=True, impl=self.impl)
         B, H, W, C = h.shape
-        h = ops.group_norm(h.view(B, H * W, C), w["conv_norm_out.weight"], w["conv_norm_out.bias"], GROUPS, 1e-5, True)
+        if ar is not None:
+            h = ops.group_norm_apply(h.view(B, H * W, C), hs, w["conv_norm_out.weight"], w["conv_norm_out.bias"], GROUPS, 1e-5, True)
+        else:
+            h = ops.group_norm(h.view(B, H * W, C), w["conv_norm_out.weight"], w["conv_norm_out.bias"], GROUPS, 1e-5, True)
         return ops.conv3x3(h.view(B, H, W, C), w["conv_out.weight"], w["conv_out.bias"], impl=self.impl)
 
     def __call__(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor,

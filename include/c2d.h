@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 1
+#define C2D_ABI_VERSION 2
 
 enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
 enum { C2D_F32 = 0, C2D_BF16 = 1 };
@@ -77,6 +77,30 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
 int c2d_group_norm(const void* x, const void* x2, const float* gamma, const float* beta, void* y, void* raw_cat,
                    double* stats_ws, int B, int HW, int C1, int C2, int groups, float eps, int silu, int dtype,
                    void* stream);
+
+/* ---- tcgen05 (bf16) GEMM / convolution with the two optional extras of the product path:
+ *  (1) A = [x | x2] concatenated along K (first K1 columns from x, K1 % 64 == 0): the UNet's skip concatenation
+ *      `torch.cat([h, skip], 1)` feeding conv_shortcut is never materialised;
+ *  (2) chan_stats != NULL: the epilogue also accumulates per-channel (sum, sum of squares) of y into
+ *      chan_stats[M / stats_rows][N][2], 2^20 fixed-point 64-bit integers (caller zero-initialises), which
+ *      c2d_group_norm_apply consumes -- the GroupNorm statistics pass over y disappears.
+ *  Same arithmetic as c2d_linear / c2d_conv3x3 otherwise.  bf16 only: fails with C2D_ERR_ARG for fp32. */
+int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w, const float* bias,
+                  const float* rowvec, int rows_per_vec, const void* residual, void* y, int M, int N, int K,
+                  int ldx, int ldy, int ldr, int act, long long* chan_stats, int stats_rows, int dtype,
+                  void* stream);
+int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual,
+                   void* y, int B, int H, int W, int Cin, int Cout, int stride, long long* chan_stats, int dtype,
+                   void* stream);
+
+/* ---- per-channel statistics of x[B][HW][C] in the format above (for tensors not produced by an _ex call). */
+int c2d_channel_stats(const void* x, long long* chan_stats, int B, int HW, int C, int dtype, void* stream);
+
+/* ---- GroupNorm (+ optional SiLU) from channel statistics: ONE pass over x (and the skip source x2, whose
+ *  statistics are stats2); same result as c2d_group_norm up to the fixed-point rounding of the sums. */
+int c2d_group_norm_apply(const void* x, const void* x2, const long long* stats1, const long long* stats2,
+                         const float* gamma, const float* beta, void* y, int B, int HW, int C1, int C2,
+                         int groups, float eps, int silu, int dtype, void* stream);
 
 /* ---- LayerNorm over the last dim of x[M][C]. */
 int c2d_layer_norm(const void* x, const float* gamma, const float* beta, void* y, int M, int C, float eps,

@@ -150,6 +150,81 @@ def test_group_norm(B, HW, C, dtype):
         assert rel(y, T.group_norm(x, g, b, 32, 1e-5, silu)) < (5e-5 if dtype == F32 else 1e-2)
 
 
+def _ref_stats(y, B):
+    """fp64 per-channel (sum, sumsq) of y [B, ..., C] in the fixed-point units of the epilogue."""
+    C = y.shape[-1]
+    yy = y.double().reshape(B, -1, C)
+    return torch.stack([yy.sum(1), (yy * yy).sum(1)], -1) * T.STATS_SCALE
+
+
+def _stats_close(stats, y, B, C):
+    got, ref = stats.view(B, C, 2).double(), _ref_stats(y, B)
+    # sums: absolute error relative to the sum of |y|; sums of squares: relative
+    assert float((got[..., 1] - ref[..., 1]).abs().max() / ref[..., 1].abs().max()) < 2e-3
+    scale = y.double().abs().reshape(B, -1, C).sum(1) * T.STATS_SCALE
+    assert float(((got[..., 0] - ref[..., 0]).abs() / scale).max()) < 2e-3
+
+
+@pytest.mark.parametrize("B,HW,N,K,K1,res", [(2, 4096, 320, 320, 0, True), (2, 1024, 640, 1920, 1280, False),
+                                             (4, 64, 1280, 2560, 1280, True), (3, 256, 200, 72, 0, False),
+                                             (2, 1024, 640, 960, 640, True), (2, 16, 1280, 1280, 0, True),
+                                             (2, 4, 1280, 2560, 1280, False)])
+def test_linear_ex_stats_and_kconcat(B, HW, N, K, K1, res):
+    """c2d_linear_ex: A = [x | x2] along K, epilogue channel statistics == statistics of the stored output."""
+    M = B * HW
+    x, w = rnd(M, K, dtype=BF16), rnd(N, K, dtype=BF16, scale=K ** -0.5, seed=1)
+    b = rnd(N, seed=2)
+    r = rnd(M, N, dtype=BF16, seed=3) if res else None
+    stats = torch.zeros(B * N * 2, device=DEV, dtype=torch.int64)
+    if K1:
+        xa, xb = x[:, :K1].contiguous(), x[:, K1:].contiguous()
+        y = ops.linear(xa, w, b, residual=r, x2=xb, stats=stats, stats_rows=HW)
+    else:
+        y = ops.linear(x, w, b, residual=r, stats=stats, stats_rows=HW)
+    ref = T.linear(x, w, b, residual=r)
+    assert rel(y, ref) < 1e-2
+    assert torch.equal(y, ops.linear(x, w, b, residual=r))          # same arithmetic as the plain entry point
+    _stats_close(stats, y, B, N)
+    # bit-reproducible: integer accumulation does not depend on CTA order
+    stats2 = torch.zeros_like(stats)
+    if K1:
+        ops.linear(xa, w, b, residual=r, x2=xb, stats=stats2, stats_rows=HW)
+    else:
+        ops.linear(x, w, b, residual=r, stats=stats2, stats_rows=HW)
+    assert torch.equal(stats, stats2)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,stride", [(2, 32, 320, 640, 1), (2, 16, 640, 320, 1), (4, 8, 1280, 1280, 1),
+                                                 (2, 32, 320, 320, 2), (1, 64, 128, 96, 1), (2, 4, 1280, 1280, 1), (2, 2, 1280, 1280, 1), (2, 4, 640, 640, 2)])
+def test_conv3x3_ex_stats(B, H, Cin, Cout, stride):
+    x = rnd(B, H, H, Cin, dtype=BF16)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), BF16)
+    b, rv = rnd(Cout, seed=2), rnd(B, Cout, seed=4)
+    Ho = H // stride
+    r = rnd(B, Ho, Ho, Cout, dtype=BF16, seed=3)
+    stats = torch.zeros(B * Cout * 2, device=DEV, dtype=torch.int64)
+    y = ops.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride, stats=stats)
+    assert torch.equal(y, ops.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride, impl=ops.IMPL_TCGEN05))
+    assert rel(y, T.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride)) < 1e-2
+    _stats_close(stats, y, B, Cout)
+
+
+@pytest.mark.parametrize("B,HW,C1,C2", [(2, 4096, 320, 0), (2, 64, 1280, 1280), (3, 256, 1280, 640), (1, 1024, 640, 320),
+                                        (16, 1024, 640, 0), (2, 4096, 640, 320), (1, 16384, 128, 0)])
+def test_group_norm_apply_from_channel_stats(B, HW, C1, C2):
+    x1 = rnd(B, HW, C1, dtype=BF16) * 2 + 0.5
+    x2 = rnd(B, HW, C2, dtype=BF16, seed=7) * 3 - 1 if C2 else None
+    C = C1 + C2
+    g, b = 1 + 0.1 * rnd(C, seed=1), 0.1 * rnd(C, seed=2)
+    s1 = ops.channel_stats(x1, torch.zeros(B * C1 * 2, device=DEV, dtype=torch.int64))
+    _stats_close(s1, x1, B, C1)
+    s2 = ops.channel_stats(x2, torch.zeros(B * C2 * 2, device=DEV, dtype=torch.int64)) if C2 else None
+    for silu in (False, True):
+        y = ops.group_norm_apply(x1, s1, g, b, 32, 1e-5, silu, x2=x2, stats2=s2)
+        assert rel(y, T.group_norm(x1, g, b, 32, 1e-5, silu, x2=x2)) < 1e-2
+        assert rel(y, ops.group_norm(x1, g, b, 32, 1e-5, silu, x2=x2)) < 4e-3      # vs the two-pass kernel
+
+
 @pytest.mark.parametrize("dtype", [F32, BF16])
 def test_group_norm_two_source(dtype):
     B, HW, C1, C2 = 2, 1024, 640, 320

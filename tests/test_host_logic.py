@@ -206,6 +206,23 @@ def test_unet_host_logic_vs_oracle(gold, W):
     assert rel_l2(eps, _t(g["eps"])) < 2e-5
 
 
+def test_unet_fused_groupnorm_host_logic_vs_oracle(gold, W):
+    """The bf16 product path's wiring (producer-side channel statistics -> one-pass GroupNorm, K-concatenated
+    shortcut GEMM) run in fp32 through the test double must reproduce the oracle UNet."""
+    g = gold("unet_16x16.npz")
+    clap = _t(PL.clap_embedding(0))[None]
+    with torch_ops.installed(), torch.no_grad():
+        unet, mgr = _build_unet(W)
+        unet.fused_gn = True
+        enc = phier.ImprovedHierarchicalAudioEncoder().eval()
+        enc.load_state_dict(W["hier"])
+        routed = enc.encode(clap, with_tokens77=False)["routed"]
+        x = _t(PL.init_noise(5, 16, 16))[None]
+        eps = unet(x, float(g["t"]), _t(PL.text_states("a beach"))[None],
+                   cross_attention_kwargs=mgr.get_audio_kwargs(routed))
+    assert rel_l2(eps, _t(g["eps"])) < 1e-4
+
+
 def test_sampler_host_logic_vs_oracle(W):
     """3 DDIM + 3 Euler steps with CFG on an 8x8 latent: product loop (hoisted tables, fused CFG/scheduler
     contract, D2 audio tiling) == oracle loop."""

@@ -18,7 +18,21 @@ from clap2diffusion_b200 import ops as real_ops
 ACT = {0: lambda v: v, 1: F.gelu, 2: F.silu}
 
 
-def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1, out=None, impl=0):
+STATS_SCALE = float(1 << 20)
+
+
+def _add_stats(stats, y, B):
+    """Mirror of the epilogue statistics: per-channel (sum, sumsq) as 2^20 fixed-point int64 [B, C, 2]."""
+    C = y.shape[-1]
+    yy = y.float().reshape(B, -1, C)
+    st = torch.stack([yy.sum(1), (yy * yy).sum(1)], -1)
+    stats.view(B, C, 2).add_(torch.round(st.double() * STATS_SCALE).to(torch.int64))
+
+
+def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1, out=None, impl=0, x2=None,
+           stats=None, stats_rows=0):
+    if x2 is not None:
+        x = torch.cat([x, x2], -1)
     y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
     if rowvec is not None:
         M = y.numel() // y.shape[-1]
@@ -27,6 +41,8 @@ def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1
     y = ACT[act](y)
     if residual is not None:
         y = y + residual.float().reshape(y.shape)
+    if stats is not None:
+        _add_stats(stats, y, (y.numel() // y.shape[-1]) // stats_rows)
     y = y.to(x.dtype)
     if out is not None:
         out.copy_(y.reshape(out.shape))
@@ -61,7 +77,8 @@ def pack_conv3x3(w, dtype):
     return w.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
-def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, upsample=False, out=None, impl=0):
+def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, upsample=False, out=None, impl=0,
+            stats=None):
     xin = x.float().permute(0, 3, 1, 2)
     if upsample:
         xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
@@ -72,6 +89,8 @@ def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, ups
     y = y.permute(0, 2, 3, 1)
     if residual is not None:
         y = y + residual.float().reshape(y.shape)
+    if stats is not None:
+        _add_stats(stats, y, y.shape[0])
     return y.contiguous().to(x.dtype)
 
 
@@ -81,6 +100,27 @@ def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_
         raw_cat.copy_(xx)
     B, C = xx.shape[0], xx.shape[-1]
     y = F.group_norm(xx.float().reshape(B, -1, C).transpose(1, 2), groups, gamma, beta, eps).transpose(1, 2)
+    if silu:
+        y = F.silu(y)
+    return y.reshape(xx.shape).contiguous().to(x.dtype)
+
+
+def channel_stats(x, stats):
+    _add_stats(stats, x, x.shape[0])
+    return stats
+
+
+def group_norm_apply(x, stats, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, stats2=None, out=None):
+    xx = x if x2 is None else torch.cat([x, x2], dim=-1)
+    B, C = xx.shape[0], xx.shape[-1]
+    st = stats.view(B, -1, 2) if stats2 is None else torch.cat([stats.view(B, -1, 2), stats2.view(B, -1, 2)], 1)
+    n = (xx.numel() // (B * C)) * (C // groups)
+    g = st.view(B, groups, C // groups, 2).sum(2).double() / STATS_SCALE / n
+    mean, var = g[..., 0], (g[..., 1] - g[..., 0] ** 2).clamp_min(0.0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    cm = mean.float().repeat_interleave(C // groups, 1)[:, None, :]
+    cr = rstd.float().repeat_interleave(C // groups, 1)[:, None, :]
+    y = (xx.float().reshape(B, -1, C) - cm) * cr * gamma + beta
     if silu:
         y = F.silu(y)
     return y.reshape(xx.shape).contiguous().to(x.dtype)

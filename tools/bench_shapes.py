@@ -106,7 +106,11 @@ def main():
             gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
             out = torch.empty(B, hw * hw, C, device=dev, dtype=bf)
             us = timeit(lambda: ops.group_norm(x, gam, bet, 32, 1e-5, True, x2=x2, out=out), a.reps)
-            print(f"  {hw * hw:5d} {c1:5d} {c2:5d}  {us:8.1f}  {3.0 * B * hw * hw * C * 2 / us / 1e3:7.1f}")
+            s1 = ops.channel_stats(x, torch.zeros(B * c1 * 2, device=dev, dtype=torch.int64))
+            s2 = ops.channel_stats(x2, torch.zeros(B * c2 * 2, device=dev, dtype=torch.int64)) if c2 else None
+            us2 = timeit(lambda: ops.group_norm_apply(x, s1, gam, bet, 32, 1e-5, True, x2=x2, stats2=s2, out=out), a.reps)
+            print(f"  {hw * hw:5d} {c1:5d} {c2:5d}  {us:8.1f}  {3.0 * B * hw * hw * C * 2 / us / 1e3:7.1f}   one-pass apply {us2:8.1f} us "
+                  f"{2.0 * B * hw * hw * C * 2 / us2 / 1e3:7.1f} GB/s")
     if "ln" in what:
         print("layer_norm: M C  us  GB/s")
         for hw, C in levels:
