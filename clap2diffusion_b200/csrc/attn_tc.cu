@@ -20,6 +20,7 @@
 // (P x ones), 8 softmax warps with a per-key-half split -- the kernel is bounded by TMEM-read + MUFU.EX2
 // throughput (ncu: pipe_tc ~58 %, xu ~50 %), not by warp-level latency hiding.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -361,7 +362,21 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   return check_launch("attn_tc");
 }
 
+bool attention_tc2_supported(const AttnParams& p, int B);
+int attention_tc2(const AttnParams& p, int B, cudaStream_t s);
+
+// C2D_ATTN=legacy keeps every shape on the first-generation kernel (A/B runs)
+static bool attn_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_ATTN");
+    v = (e && e[0] == 'l') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int attention_tc(const AttnParams& p, int B, cudaStream_t s) {
+  if (!attn_legacy() && attention_tc2_supported(p, B)) return attention_tc2(p, B, s);
   CUtensorMap tq, tk, tv;
   int rc = make_head_tmap(&tq, p.q, p.d, p.heads, p.Nq, B, p.ldq, p.bsq, AT_BQ);
   if (rc) return rc;

@@ -11,6 +11,20 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  tcgen05.mma / cp.async.bulk.tensor / tcgen05.commit are uniform-datapath
+// instructions: issued under this predicate from warp-uniform code, ptxas keeps their descriptors in uniform
+// registers; issued from an `if (lane == 0)` region it wraps every one of them in a lane-serialising loop with
+// several R2UR moves (~65 cycles per MMA measured on B200), which makes the issuing thread the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -259,7 +259,8 @@ def test_attention_simt(B, h, Nq, Nkv, d, dtype):
 
 
 ATT_TC = [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160), (3, 8, 64, 64, 160),
-          (2, 8, 4096, 77, 40), (2, 8, 1024, 81, 80), (1, 8, 256, 77, 160), (2, 4, 200, 333, 64), (1, 2, 130, 129, 16)]
+          (2, 8, 4096, 77, 40), (2, 8, 1024, 81, 80), (1, 8, 256, 77, 160), (2, 4, 200, 333, 64), (1, 2, 130, 129, 16),
+          (1, 3, 700, 1000, 48), (2, 2, 256, 256, 24), (1, 1, 1, 257, 64)]
 
 
 @pytest.mark.parametrize("B,h,Nq,Nkv,d", ATT_TC)
