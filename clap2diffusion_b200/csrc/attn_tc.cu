@@ -102,74 +102,89 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + AT_SB * AT_BK;
 
+  // producer and MMA warps run converged and issue through elect_one() (see tc_common.cuh)
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer =====================
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(smem + Cfg::OFF_Q + blk * AT_QTILE, &tmQ, q_full, blk * 64, h, q0, b);
-      for (int t = 0; t < ntiles; ++t) {
-        {
-          const int s = t % KS;
-          mbar_wait(&k_empty[s], ((uint32_t)(t / KS) & 1u) ^ 1u);
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; ++t) {
+      {
+        const int s = t % KS;
+        mbar_wait(&k_empty[s], ((uint32_t)(t / KS) & 1u) ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&k_full[s], Cfg::KV_BYTES);
 #pragma unroll
           for (int blk = 0; blk < NBLK; ++blk)
             tma_load_4d(smem + Cfg::OFF_K + (s * NBLK + blk) * AT_KTILE, &tmK, &k_full[s], blk * 64, h, t * AT_BK, b);
         }
-        {
-          const int s = t % VS;
-          mbar_wait(&v_empty[s], ((uint32_t)(t / VS) & 1u) ^ 1u);
+        __syncwarp();
+      }
+      {
+        const int s = t % VS;
+        mbar_wait(&v_empty[s], ((uint32_t)(t / VS) & 1u) ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&v_full[s], Cfg::KV_BYTES);
 #pragma unroll
           for (int blk = 0; blk < NBLK; ++blk)
             tma_load_4d(smem + Cfg::OFF_V + (s * NBLK + blk) * AT_KTILE, &tmV, &v_full[s], blk * 64, h, t * AT_BK, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc_qk = make_idesc_bf16(128, AT_BK, 0, 0);
-      const uint32_t idesc_pv = make_idesc_bf16(128, p.npv, 0, 1);          // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(smem + Cfg::OFF_Q);
-      const int ksteps = (p.d + 15) >> 4;
-      auto issue_qk = [&](int t) {
-        const int s = t % KS;
-        mbar_wait(&k_full[s], (uint32_t)(t / KS) & 1u);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(smem + Cfg::OFF_K + s * Cfg::KV_BYTES);
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_qk = make_idesc_bf16(128, AT_BK, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(128, p.npv, 0, 1);          // B (= V) is MN-major
+    const uint64_t q_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_Q));
+    const uint64_t k_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_K));
+    const uint64_t p_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_P));
+    const uint64_t v_desc = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_V), AT_KTILE, 1024);
+    const int ksteps = (p.d + 15) >> 4;
+    auto issue_qk = [&](int t) {
+      const int s = t % KS;
+      mbar_wait(&k_full[s], (uint32_t)(t / KS) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t tmem_s = tmem_base + (uint32_t)(t & 1) * AT_BK;
+        const uint64_t kd = k_desc + (uint64_t)(s * (Cfg::KV_BYTES >> 4));
         for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t koff = (uint32_t)(kk & 3) * 32;
-          umma_f16(tmem_s, make_desc_k_sw128(q_addr + (uint32_t)(kk >> 2) * AT_QTILE + koff),
-                   make_desc_k_sw128(k_addr + (uint32_t)(kk >> 2) * AT_KTILE + koff), idesc_qk, kk > 0 ? 1u : 0u);
+          // 64-column blocks are AT_QTILE / AT_KTILE bytes apart; +32 B per K = 16 step inside the swizzle row
+          const uint64_t qo = (uint64_t)((kk >> 2) * (AT_QTILE >> 4) + (kk & 3) * 2);
+          const uint64_t ko = (uint64_t)((kk >> 2) * (AT_KTILE >> 4) + (kk & 3) * 2);
+          umma_f16(tmem_s, q_desc + qo, kd + ko, idesc_qk, kk > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[t & 1]);
         umma_commit(&k_empty[s]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      if (ntiles > 1) issue_qk(1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int pb = j & 1, vs = j % VS;
-        mbar_wait(&p_full[pb], (uint32_t)(j >> 1) & 1u);     // P(j) written, S(j) consumed
-        mbar_wait(&v_full[vs], (uint32_t)(j / VS) & 1u);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + Cfg::OFF_P + pb * AT_QTILE);
-        const uint32_t v_addr = smem_u32(smem + Cfg::OFF_V + vs * Cfg::KV_BYTES);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (ntiles > 1) issue_qk(1);
+    for (int j = 0; j < ntiles; ++j) {
+      const int pb = j & 1, vs = j % VS;
+      mbar_wait(&p_full[pb], (uint32_t)(j >> 1) & 1u);     // P(j) written, S(j) consumed
+      mbar_wait(&v_full[vs], (uint32_t)(j / VS) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t pd = p_desc + (uint64_t)(pb * (AT_QTILE >> 4));
+        const uint64_t vd = v_desc + (uint64_t)(vs * (Cfg::KV_BYTES >> 4));
 #pragma unroll
         for (int kk = 0; kk < AT_BK / 16; ++kk) {
           // V tile: [64 keys][64-col blocks]; 16 keys = 2 groups of 8 rows (SBO = 1024 B), col blocks 8 KB apart (LBO)
-          umma_f16(tmem_o, make_desc_k_sw128(p_addr + (uint32_t)kk * 32),
-                   make_desc_mn_sw128(v_addr + (uint32_t)kk * 2048, AT_KTILE, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_f16(tmem_o, pd + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&p_empty[pb]);
         umma_commit(&v_empty[vs]);
-        // refill the S buffer that softmax(j) released.  (After PV(j), never before: the producer may need
-        // v_empty from PV(j) before it can reach K(j+2).)
-        if (j + AT_SB < ntiles) issue_qk(j + AT_SB);
       }
+      __syncwarp();
+      // refill the S buffer that softmax(j) released.  (After PV(j), never before: the producer may need
+      // v_empty from PV(j) before it can reach K(j+2).)
+      if (j + AT_SB < ntiles) issue_qk(j + AT_SB);
     }
   } else {
     // ===================== softmax / correction / epilogue (warps 2..5) =====================

@@ -159,20 +159,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run their protocols CONVERGED and issue through elect_one(): the TMA / tcgen05
+  // instructions are uniform-datapath instructions and must not sit in a lane-divergent region (tc_common.cuh).
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int b0 = 0, y0 = 0, x0 = 0;
-      if (CONV) {
-        b0 = m0 / p.HW;
-        int rem = m0 - b0 * p.HW;
-        y0 = rem / p.W;
-        x0 = rem - y0 * p.W;
-      }
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
+    // ===================== TMA producer =====================
+    int b0 = 0, y0 = 0, x0 = 0;
+    if (CONV) {
+      b0 = m0 / p.HW;
+      int rem = m0 - b0 * p.HW;
+      y0 = rem / p.W;
+      x0 = rem - y0 * p.W;
+    }
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      if (elect_one()) {
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -189,27 +191,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t a_desc = make_desc_k_sw128(a_addr);
-        const uint64_t b_desc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
+    const uint64_t desc0 = make_desc_k_sw128(smem_u32(smem));
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        // descriptor address field is in 16-byte units; +2 per K = 16 step inside the 128-byte swizzle row
+        const uint64_t a_desc = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
+        const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+        for (int k = 0; k < TC_BK / 16; ++k)
           umma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty[s]);          // smem slot reusable once these MMAs retire
+        umma_commit(&empty[s]);                                   // smem slot reusable once these MMAs retire
+        if (kb == p.num_k_blocks - 1) umma_commit(tmem_full);     // accumulator complete
       }
-      umma_commit(tmem_full);            // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -426,21 +429,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer (runs ahead across tiles) =====================
-      uint32_t kbc = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
-        int b0 = 0, y0 = 0, x0 = 0;
-        if (CONV) {
-          b0 = m0 / p.HW;
-          const int rem = m0 - b0 * p.HW;
-          y0 = rem / p.W;
-          x0 = rem - y0 * p.W;
-        }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
-          const int s = kbc % STAGES;
-          mbar_wait(&empty[s], ((kbc / STAGES) & 1u) ^ 1u);
+    // ===================== TMA producer (runs ahead across tiles; converged warp, elected lane issues) =====================
+    uint32_t kbc = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
+      int b0 = 0, y0 = 0, x0 = 0;
+      if (CONV) {
+        b0 = m0 / p.HW;
+        const int rem = m0 - b0 * p.HW;
+        y0 = rem / p.W;
+        x0 = rem - y0 * p.W;
+      }
+      for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
+        const int s = kbc % STAGES;
+        mbar_wait(&empty[s], ((kbc / STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -456,31 +459,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
-      uint32_t kbc = 0, it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        mbar_wait(&tempty[buf], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
+    const uint64_t desc0 = make_desc_k_sw128(smem_u32(smem));
+    uint32_t kbc = 0, it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(&tempty[buf], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
+        const int s = kbc % STAGES;
+        mbar_wait(&full[s], (kbc / STAGES) & 1u);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
-          const int s = kbc % STAGES;
-          mbar_wait(&full[s], (kbc / STAGES) & 1u);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint64_t a_desc = make_desc_k_sw128(a_addr);
-          const uint64_t b_desc = make_desc_k_sw128(a_addr + Cfg::A_BYTES);
+        if (elect_one()) {
+          const uint64_t a_desc = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
+          const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_f16(acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[s]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&tfull[buf]);
         }
-        umma_commit(&tfull[buf]);
+        __syncwarp();
       }
     }
   } else {
@@ -635,16 +640,288 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
+// =====================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on the two SMs of a TPC computes a 256 x BN tile.
+// Each CTA TMA-loads its own 128 A rows and HALF of the B rows (BN / 2) and keeps its own 128 x BN fp32
+// accumulator in TMEM; the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both.  Per SM and
+// k-block that is (128 + BN/2) x 64 operand elements through shared memory instead of (128 + BN) x 64: the
+// single-CTA SS MMA saturates the 128 B/clk shared-memory port at ~55 % tensor utilisation (measured), the pair
+// does not.  Pipeline protocol: every CTA's producer waits on its OWN empty[s] (armed in both CTAs by the leader's
+// multicast commit), all TMA bytes of a stage are counted on the LEADER's full[s]; two clusters are co-resident
+// per SM pair so one tile's epilogue overlaps the other's main loop.
+// =====================================================================================================
+template <int BN, int STAGES>
+struct Tc3Cfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int EPI_PITCH = 36;                                          // floats per staged row (32 + pad)
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                      // aliases pipeline stage 0
+  static constexpr int OFF_BIAS = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(EPI_BYTES <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
+};
+
+template <int BN, int STAGES, bool CONV, bool GEGLU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_n) {
+  using Cfg = Tc3Cfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int m0 = ((pair / num_n) * 2 + (int)rank) * TC_BM, n0 = (pair % num_n) * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                       // barrier inits and the TMEM allocation are visible to the peer CTA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; converged warp, elected lane issues) =====================
+    int b0 = 0, y0 = 0, x0 = 0;
+    if (CONV) {
+      b0 = m0 / p.HW;
+      int rem = m0 - b0 * p.HW;
+      y0 = rem / p.W;
+      x0 = rem - y0 * p.W;
+    }
+    const int nb = n0 + (int)rank * (BN / 2);          // this CTA's half of the B rows
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      if (elect_one()) {
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);      // both CTAs' bytes land here
+        const uint32_t lbar = mapa_rank0(smem_u32(&full[s]));
+        if (CONV) {
+          const int tap = kb / p.cblocks;
+          const int c0 = (kb - tap * p.cblocks) * TC_BK;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          tma_load_4d_2sm(sA, &tmA, lbar, c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
+          tma_load_2d_2sm(sB, &tmB, lbar, tap * p.Cin + c0, nb);
+        } else {
+          if (kb < p.kb_split) tma_load_2d_2sm(sA, &tmA, lbar, kb * TC_BK, m0);
+          else tma_load_2d_2sm(sA, &tmA2, lbar, (kb - p.kb_split) * TC_BK, m0);
+          tma_load_2d_2sm(sB, &tmB, lbar, kb * TC_BK, nb);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 0, 0);
+      const uint64_t desc0 = make_desc_k_sw128(smem_u32(smem));
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
+          const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_f16_2sm(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);                                   // frees the slot in both CTAs
+          if (kb == p.num_k_blocks - 1) umma_commit_2sm(tmem_full);     // both accumulators complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)q * 32 * Cfg::EPI_PITCH;
+    const int ncols = GEGLU ? (p.N >> 1) : p.N;
+    const int nbase = GEGLU ? (n0 >> 1) : n0;
+    const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+    const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
+    {
+      const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
+      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        const int n = n0 + j;
+        float bv = 0.f;
+        if (n < p.N) {
+          if (p.bias) bv = __ldg(p.bias + n);
+          if (rv0) bv += __ldg(rv0 + n);
+        }
+        s_bias[j] = bv;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    mbar_wait(tmem_full, 0);      // all MMAs retired: the pipeline smem of BOTH CTAs is idle (staging aliases stage 0)
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int NCHUNK = GEGLU ? BN / 64 : BN / 32;
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      // ---- TMEM -> registers -> (+bias, activation | GEGLU gate) -> per-warp fp32 staging [32 rows][32 cols]
+      float v[32];
+      if (!GEGLU) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c * 32 + j];
+        if (p.rowvec && !rv_shared) {
+          const int m = m0 + q * 32 + lane;
+          if (m < p.M) {
+            const float* rv = p.rowvec + (long long)(m / p.rows_per_vec) * p.N + n0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + c * 32 + j < p.N) v[j] += __ldg(rv + j);
+          }
+        }
+        if (p.act != C2D_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+      } else {
+        // accumulator columns: 128-column groups of [a (64) | gate (64)]; output chunk c covers 32 outputs
+        const int grp = c >> 1, sub = c & 1;
+        uint32_t ra[32], rg[32];
+        tmem_ld_32x32(t_row + grp * 128 + sub * 32, ra);
+        tmem_ld_32x32(t_row + grp * 128 + 64 + sub * 32, rg);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float a = __uint_as_float(ra[j]) + s_bias[grp * 128 + sub * 32 + j];
+          const float g = __uint_as_float(rg[j]) + s_bias[grp * 128 + 64 + sub * 32 + j];
+          v[j] = a * gelu_erf(g);
+        }
+      }
+      float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      // ---- coalesced drain: 32 rows x 4 groups of 8 columns; residual loads of all 4 items issued first
+      uint4 res[4];
+      const int rsub = lane >> 2, g = lane & 3;
+      const int mrow0 = m0 + q * 32;
+      const int n = nbase + c * 32 + g * 8;
+      const int nvalid = ncols - n;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int m = mrow0 + u * 8 + rsub;
+        res[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (m < p.M && vec_r && nvalid >= 8) res[u] = *reinterpret_cast<const uint4*>(p.residual + (long long)m * p.ldr + n);
+      }
+      float ssum[8], ssq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = u * 8 + rsub, m = mrow0 + rr;
+        if (m >= p.M || nvalid <= 0) continue;
+        const float* sp = stage + (size_t)rr * Cfg::EPI_PITCH + g * 8;
+        const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
+        float o[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        bf16* yp = p.y + (long long)m * p.ldy + n;
+        if (p.residual) {
+          if (vec_r && nvalid >= 8) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&res[u]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(hh[j]); o[2 * j] += f.x; o[2 * j + 1] += f.y; }
+          } else {
+            const bf16* rp = p.residual + (long long)m * p.ldr + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (j < nvalid) o[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (vec_y && nvalid >= 8) {
+          Vec8<bf16>::store(yp, o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+      }
+      if (p.stats && mrow0 < p.M) {
+        const int bimg = mrow0 / p.stats_rows;
+        stats_commit(ssum, ssq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();             // the peer may still read this CTA's smem / TMEM until its last MMA has retired
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES, bool CONV, bool GEGLU>
+static int launch_tc3(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+  using Cfg = Tc3Cfg<BN, STAGES>;
+  static_assert(Cfg::SMEM_BYTES <= 113 * 1024, "two CTAs per SM");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<BN, STAGES, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc3: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return C2D_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int num_n = ceil_div(p.N, BN);
+  const int pairs = num_n * ceil_div(ceil_div(p.M, TC_BM), 2);
+  gemm_tc3_kernel<BN, STAGES, CONV, GEGLU><<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_n);
+  return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
+}
+
 // Kernel selection.  Measured on B200 (tools/bench_shapes.py): the persistent kernel wins on the GEGLU projection
 // (N = 8C, short K: +20 %), the two-CTA-per-SM kernel wins elsewhere (two MMA issuers hide each other's
 // barrier round trips).  C2D_GEMM=legacy | persistent forces one of them for A/B runs.
-static int gemm_mode() {           // 0 = auto, 1 = legacy, 2 = persistent
+static int gemm_mode() {           // 0 = auto, 1 = legacy, 2 = persistent, 3 = CTA pair (cta_group::2)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("C2D_GEMM");
-    v = !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 'p' ? 2 : 0));
+    v = !e ? 0 : (e[0] == 'l' ? 1 : (e[0] == 'p' ? 2 : (e[0] == '2' ? 3 : 0)));
   }
   return v;
+}
+// auto: the CTA-pair kernel for the 3x3 convolutions (long K, operand-bandwidth bound: +8..35 % measured), the
+// two-CTA-per-SM single-CTA kernel for plain linears (short K: the pair's cluster syncs cost more than they save)
+static bool use_pair(bool conv = false) {
+  const int m = gemm_mode();
+  return m == 3 || (m == 0 && conv);
+}
+// B-tile width of the pair kernel: N % 32 == 0 for M = 256 MMAs
+static int pick_bn_pair(int N) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("C2D_PAIR_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 128 || (forced == 160 && N % 160 == 0) || (forced == 256 && N % 256 == 0)) return forced;
+  if (N % 160 == 0) return 160;               // measured best on every UNet shape (BN = 256 leaves too few CTAs)
+  if (N % 256 == 0) return 256;
+  return 128;
 }
 static bool use_persistent(bool geglu = false) {
   const int m = gemm_mode();
@@ -678,7 +955,9 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   if (ex && ex->stats)
     C2D_REQUIRE(!geglu && ex->stats_rows > 0 && ex->stats_rows % 32 == 0 && M % ex->stats_rows == 0,
                 "linear_tc: channel statistics need rows-per-image %% 32 == 0 (M=%d stats_rows=%d)", M, ex->stats_rows);
-  const int BN = geglu ? 128 : (use_persistent(geglu) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128));
+  const bool pairk = use_pair();
+  const int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
+                       : (geglu ? 128 : (use_persistent(geglu) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
   CUtensorMap tmA, tmA2, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
@@ -699,7 +978,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t st[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {TC_BK, (uint32_t)BN};
+    uint32_t box[2] = {TC_BK, (uint32_t)(pairk ? BN / 2 : BN)};
     int rc = make_tmap_bf16(&tmB, w, 2, dims, st, box);
     if (rc) return rc;
   }
@@ -712,6 +991,12 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   p.kb_split = cat ? K1 / TC_BK : p.num_k_blocks;
   p.stats = ex ? reinterpret_cast<unsigned long long*>(ex->stats) : nullptr;
   p.stats_rows = ex && ex->stats ? ex->stats_rows : 1;
+  if (pairk) {
+    if (geglu) return BN == 256 ? launch_tc3<256, 3, false, true>(tmA, tmA2, tmB, p, s) : launch_tc3<128, 4, false, true>(tmA, tmA2, tmB, p, s);
+    if (BN == 256) return launch_tc3<256, 3, false, false>(tmA, tmA2, tmB, p, s);
+    if (BN == 160) return launch_tc3<160, 4, false, false>(tmA, tmA2, tmB, p, s);
+    return launch_tc3<128, 4, false, false>(tmA, tmA2, tmB, p, s);
+  }
   if (use_persistent(geglu)) {
     if (geglu) return launch_tc2<128, 6, false, true>(tmA, tmA2, tmB, p, s);
     if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmA2, tmB, p, s);
@@ -741,7 +1026,8 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   const int bw = Wo < 128 ? Wo : 128;
   const int bh = (128 / bw) < Ho ? (128 / bw) : Ho;
   const int bb = 128 / (bw * bh);
-  const int BN = use_persistent() ? pick_bn(B * Ho * Wo, Cout) : ((Cout % 160 == 0) ? 160 : 128);
+  const bool pairk = use_pair(true);
+  const int BN = pairk ? pick_bn_pair(Cout) : (gemm_mode() == 2 ? pick_bn(B * Ho * Wo, Cout) : ((Cout % 160 == 0) ? 160 : 128));
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -755,7 +1041,7 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   {
     uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
     uint64_t st[1] = {(uint64_t)9 * Cin * 2};
-    uint32_t box[2] = {TC_BK, (uint32_t)BN};
+    uint32_t box[2] = {TC_BK, (uint32_t)(pairk ? BN / 2 : BN)};
     int rc = make_tmap_bf16(&tmB, w, 2, dims, st, box);
     if (rc) return rc;
   }
@@ -770,7 +1056,12 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   if (stats) C2D_REQUIRE((Ho * Wo) % 32 == 0, "conv3x3_tc: channel statistics need Ho*Wo %% 32 == 0 (%d)", Ho * Wo);
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   p.stats_rows = Ho * Wo;
-  if (use_persistent()) {
+  if (pairk) {
+    if (BN == 256) return launch_tc3<256, 3, true, false>(tmA, tmA, tmB, p, s);
+    if (BN == 160) return launch_tc3<160, 4, true, false>(tmA, tmA, tmB, p, s);
+    return launch_tc3<128, 4, true, false>(tmA, tmA, tmB, p, s);
+  }
+  if (gemm_mode() == 2) {
     if (BN == 160) return launch_tc2<160, 5, true, false>(tmA, tmA, tmB, p, s);
     if (BN == 64) return launch_tc2<64, 8, true, false>(tmA, tmA, tmB, p, s);
     return launch_tc2<128, 6, true, false>(tmA, tmA, tmB, p, s);
