@@ -184,12 +184,34 @@ def run_ncu_step(args):
 
 
 def run_kernels(args):
-    """`--kernels`: per-kernel CUDA-event table of one eager UNet step (quick iteration aid)."""
+    """`--kernels`: per-kernel CUDA-event table of one eager UNet step (quick iteration aid); `--vae` adds the decoder."""
     import contextlib
+    from clap2diffusion_b200 import ops
     from clap2diffusion_b200.pipeline import AudioToImagePipeline
     dev = torch.device("cuda", 0)
     with contextlib.redirect_stdout(sys.stderr):
-        pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16, with_vae=False)
+        pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16, with_vae=args.vae)
+    if args.vae:
+        z = torch.randn(args.micro_batch, 4, LATENT, LATENT, device=dev)
+        for _ in range(2):
+            pipe.vae.decode(z)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pipe.vae.decode(z); e1.record(); torch.cuda.synchronize()
+        print(f"VAE decode (batch {args.micro_batch}) wall: {e0.elapsed_time(e1):.3f} ms")
+        ops.PROFILE = []
+        pipe.vae.decode(z)
+        torch.cuda.synchronize()
+        rec, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for name, flops, nbytes, a0, a1 in rec:
+            a = agg.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            a["ms"] += a0.elapsed_time(a1); a["flops"] += flops; a["bytes"] += nbytes; a["launches"] += 1
+        total = sum(a["ms"] for a in agg.values())
+        print(f"VAE decode timed-op sum: {total:.3f} ms")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            tf = f"{a['flops'] / (a['ms'] * 1e-3) / 1e12:7.1f} TF/s" if a["flops"] else "            "
+            print(f"  {k:18s} {a['ms']:8.3f} ms  {100 * a['ms'] / total:5.1f}%  x{a['launches']:<4d} {tf}  {a['bytes'] / (a['ms'] * 1e-3) / 1e9:8.1f} GB/s")
     agg = per_kernel_profile(pipe, args.micro_batch)
     total = sum(a["ms"] for a in agg.values())
     print(f"UNet step (batch {2 * args.micro_batch}) eager sum: {total:.3f} ms")
@@ -351,6 +373,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--micro-batch", type=int, default=8)
     ap.add_argument("--kernels", action="store_true", help="print the per-kernel CUDA-event table of one UNet step")
+    ap.add_argument("--vae", action="store_true", help="with --kernels: also time the VAE decoder")
     ap.add_argument("--ncu-step", action="store_true", help="profile one eager UNet step (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.ncu_step:

@@ -74,7 +74,8 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
 
 int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w, const float* bias, const float* rowvec,
                   int rows_per_vec, const void* residual, void* y, int M, int N, int K, int ldx, int ldy, int ldr, int act,
-                  long long* chan_stats, int stats_rows, int dtype, void* stream) {
+                  long long* chan_stats, int stats_rows, long long* row_stats_out, const long long* ln_row_stats,
+                  const float* ln_colsum, float ln_eps, int dtype, void* stream) {
   C2D_REQUIRE(x && w && y, "linear_ex: null pointer");
   C2D_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N, "linear_ex: bad dims M=%d N=%d K=%d ldy=%d", M, N, K, ldy);
   C2D_REQUIRE(!residual || ldr >= N, "linear_ex: bad residual stride %d", ldr);
@@ -85,11 +86,22 @@ int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w
   if (chan_stats) C2D_REQUIRE(stats_rows > 0 && M % stats_rows == 0, "linear_ex: M=%d is not a multiple of stats_rows=%d", M, stats_rows);
   // the epilogue reduction needs whole warps (32 rows) inside one image; tiny planes take the stand-alone kernel
   const bool fused = chan_stats && stats_rows % 32 == 0;
-  GemmExtras ex = {x2, K1, ldx2, fused ? chan_stats : nullptr, stats_rows};
+  C2D_REQUIRE(!ln_row_stats || ln_colsum, "linear_ex: folded LayerNorm needs ln_colsum");
+  GemmExtras ex = {x2, K1, ldx2, fused ? chan_stats : nullptr, stats_rows, row_stats_out, ln_row_stats, ln_colsum, ln_eps};
   int rc = linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, &ex, (cudaStream_t)stream);
   if (rc || !chan_stats || fused) return rc;
   C2D_REQUIRE(ldy == N, "linear_ex: channel statistics of a strided output need stats_rows %% 32 == 0");
   return c2d_channel_stats(y, chan_stats, M / stats_rows, stats_rows, N, dtype, stream);
+}
+
+int c2d_geglu_linear_ex(const void* x, const void* w, const float* bias, const long long* ln_row_stats, const float* ln_colsum,
+                        float ln_eps, void* y, int M, int F, int K, int dtype, void* stream) {
+  C2D_REQUIRE(x && w && y && M > 0 && F > 0 && K > 0, "geglu_linear_ex: bad args");
+  C2D_REQUIRE(dtype == C2D_BF16 && F % 64 == 0, "geglu_linear_ex: bf16 with F %% 64 == 0 (packed weights, c2d_pack_geglu)");
+  C2D_REQUIRE(linear_tc_supported(x, w, M, 2 * F, K, K), "geglu_linear_ex: K %% 8 / alignment");
+  C2D_REQUIRE(!ln_row_stats || ln_colsum, "geglu_linear_ex: folded LayerNorm needs ln_colsum");
+  GemmExtras ex = {nullptr, 0, 0, nullptr, 0, nullptr, ln_row_stats, ln_colsum, ln_eps};
+  return linear_tc(x, w, bias, nullptr, 1, nullptr, y, M, 2 * F, K, K, F, 0, C2D_ACT_NONE, true, &ex, (cudaStream_t)stream);
 }
 
 int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y,

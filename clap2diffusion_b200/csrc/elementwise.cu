@@ -203,6 +203,32 @@ __global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
+// LayerNorm folded into the following linear layer (one warp per output row n):
+//   w'[n][k] = w[n][k] * gamma[k]     colsum[n] = sum_k round_bf16(w'[n][k])     bias'[n] = bias[n] + sum_k beta[k] w[n][k]
+// so that  LN(x) W^T + b  =  rstd (x W'^T - mean colsum) + bias'.  colsum is taken over the ROUNDED weights the tensor
+// core will multiply, so the mean term cancels exactly what the GEMM accumulates.
+template <typename T>
+__global__ void pack_lnfold_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ bias, T* __restrict__ wo, float* __restrict__ colsum,
+                                   float* __restrict__ bo, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[(long long)n * K + k];
+    const float wg = wv * gamma[k];
+    wo[(long long)n * K + k] = from_f<T>(wg);
+    cs += __bfloat162float(__float2bfloat16_rn(wg));
+    bs = fmaf(beta[k], wv, bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bo[n] = bs + (bias ? bias[n] : 0.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // AudioAttnProcessor context step (one CTA per batch element).  See c2d.h.
 //   g[k][j]   = gelu(W1[j,:] . a[b,k,:] + b1[j])                       k < K, j < Hb
@@ -357,6 +383,15 @@ int c2d_pack_geglu(const float* w, const float* bias, void* w_out, float* bias_o
   int g = ew_grid(2LL * F * K, 256);
   DISPATCH_T(dtype, pack_geglu_kernel<T><<<g, 256, 0, (cudaStream_t)stream>>>(w, bias, (T*)w_out, bias_out, F, K);)
   return check_launch("pack_geglu");
+}
+
+int c2d_pack_lnfold(const float* w, const float* gamma, const float* beta, const float* bias, void* w_out, float* colsum,
+                    float* bias_out, int N, int K, int dtype, void* stream) {
+  C2D_REQUIRE(w && gamma && beta && w_out && colsum && bias_out && N > 0 && K > 0, "pack_lnfold: bad args");
+  const int threads = 256, rows_per_cta = threads / 32;
+  DISPATCH_T(dtype, pack_lnfold_kernel<T><<<ceil_div(N, rows_per_cta), threads, 0, (cudaStream_t)stream>>>(
+                        w, gamma, beta, bias, (T*)w_out, colsum, bias_out, N, K);)
+  return check_launch("pack_lnfold");
 }
 
 int c2d_audio_context(const void* ehs, const void* audio, const void* w1, const float* b1, const void* w2,

@@ -22,7 +22,10 @@ namespace c2d {
 
 using namespace tc;
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_THREADS = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue: TWO warps per TMEM lane quadrant that take alternate
+// 32-column chunks -- the short-K GEMMs of the UNet (K = 320) are epilogue-bound, a second warp per scheduler doubles the
+// epilogue's issue rate and its loads in flight
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 3, TC_EPI_WARPS = 8, TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 struct TcParams {
   const float* bias;
@@ -42,7 +45,58 @@ struct TcParams {
   int stats_rows;
   // plain GEMM with A = [x | x2] concatenated along K: k-blocks >= kb_split come from the second tensor map
   int kb_split;
+  // LayerNorm folded into this GEMM (consumer side): x is the UN-normalised activation, w = W diag(gamma),
+  // y = rstd_m (acc - mean_m colsum_n) + bias_n with (mean, rstd) from ln_stats[m] = fixed-point (sum, sumsq) of row m
+  const long long* ln_stats;
+  const float* ln_colsum;
+  float ln_invK, ln_eps;
+  // producer side of the same scheme: per-row fixed-point (sum, sumsq) of y accumulated over the N tiles
+  unsigned long long* rowstats_out;
 };
+
+// raw fixed-point (sum, sumsq) of row m (zero when there is no folded LayerNorm / the row is out of range); split from
+// the arithmetic so that the 16-byte load can be issued a whole tile ahead of its use
+__device__ __forceinline__ longlong2 ln_row_load(const TcParams& p, int m) {
+  longlong2 v = make_longlong2(0, 0);
+  if (p.ln_stats && m < p.M) v = *reinterpret_cast<const longlong2*>(p.ln_stats + 2 * (long long)m);
+  return v;
+}
+__device__ __forceinline__ void ln_row_finish(const TcParams& p, const longlong2& v, float& rstd, float& mr) {
+  rstd = 1.f; mr = 0.f;
+  if (p.ln_stats) {
+    const float inv = p.ln_invK * (1.0f / 1048576.0f);
+    const float mean = (float)v.x * inv;
+    const float var = fmaxf(fmaf(-mean, mean, (float)v.y * inv), 0.f);
+    rstd = rsqrtf(var + p.ln_eps);
+    mr = mean * rstd;
+  }
+}
+// out[j] = acc[j] + bias[j]  |  folded LayerNorm: rstd * acc[j] - (mean * rstd) * colsum[j] + bias[j]; bias / colsum are
+// 16-byte aligned smem slices read as float4 (the epilogue of the short-K GEMMs is instruction-bound)
+template <bool LN>
+__device__ __forceinline__ void epi_affine32(const uint32_t (&r)[32], const float* __restrict__ sb, const float* __restrict__ scs,
+                                             float rstd, float nmr, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
+    if (LN) {
+      const float4 c4 = *reinterpret_cast<const float4*>(scs + j);
+      v[j] = fmaf(__uint_as_float(r[j]), rstd, fmaf(nmr, c4.x, b4.x));
+      v[j + 1] = fmaf(__uint_as_float(r[j + 1]), rstd, fmaf(nmr, c4.y, b4.y));
+      v[j + 2] = fmaf(__uint_as_float(r[j + 2]), rstd, fmaf(nmr, c4.z, b4.z));
+      v[j + 3] = fmaf(__uint_as_float(r[j + 3]), rstd, fmaf(nmr, c4.w, b4.w));
+    } else {
+      v[j] = __uint_as_float(r[j]) + b4.x;
+      v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+      v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+    }
+  }
+}
+
+__device__ __forceinline__ void ln_row_coeffs(const TcParams& p, int m, float& rstd, float& mr) {
+  ln_row_finish(p, ln_row_load(p, m), rstd, mr);
+}
 
 constexpr float STATS_SCALE = 1048576.0f;      // 2^20
 
@@ -131,8 +185,8 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = TC_STAGES * STAGE_BYTES + 256 + 2 * BN * 4 + 1024;   // + barriers + bias/rowvec + slack
 };
 
-template <int BN, bool CONV, bool GEGLU>
-__global__ void __launch_bounds__(TC_THREADS)
+template <int BN, bool CONV, bool GEGLU, bool LNF>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   using Cfg = TcCfg<BN>;
@@ -220,25 +274,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // pipeline smem -> coalesced pass: 16-byte residual loads and bf16 stores along rows.  Each warp stages
     // and drains only its own 32 rows, so a __syncwarp is the only synchronisation.
     const int q = warp & 3;              // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;    // which of the quadrant's two warps: chunks c = half, half + 2, ...
     constexpr int NOUT = GEGLU ? BN / 2 : BN;         // output columns this CTA produces
     constexpr int PITCH = NOUT + 4;                   // floats; rows stay 16 B aligned, 16 B writes conflict-free
     // while the main loop runs: this CTA's slice of bias (+ time-embedding row vector when it is shared by the
     // whole tile) -> smem, so the drain below issues no dependent global loads for them
     float* s_bias = reinterpret_cast<float*>(smem + TC_STAGES * Cfg::STAGE_BYTES + 256);
+    float* s_cs = s_bias + BN;                            // folded-LayerNorm column sums
     const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
     {
       const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
-      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+      for (int j = threadIdx.x - 64; j < BN; j += 32 * TC_EPI_WARPS) {
         const int n = n0 + j;
-        float b = 0.f;
+        float b = 0.f, cs = 0.f;
         if (n < p.N) {
           if (p.bias) b = __ldg(p.bias + n);
           if (rv0) b += __ldg(rv0 + n);
+          if (p.ln_colsum) cs = __ldg(p.ln_colsum + n);
         }
         s_bias[j] = b;
+        s_cs[j] = cs;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");      // epilogue warps only
     }
+    float ln_rstd = 1.f, ln_mr = 0.f;
+    if (LNF) ln_row_coeffs(p, m0 + (warp & 3) * 32 + lane, ln_rstd, ln_mr);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     float* stage = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * PITCH;
@@ -249,25 +309,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* srow = stage + (size_t)lane * PITCH;
       if (!GEGLU) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld_32x32(t_row + c * 32, r);
           tmem_ld_wait();
           const int n = n0 + c * 32;
           float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + j);
-            v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-          }
+          epi_affine32<LNF>(r, s_bias + c * 32, s_cs + c * 32, ln_rstd, -ln_mr, v);
           if (rv) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rv + n + j);
           }
           if (p.act != C2D_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -275,18 +330,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {
         // GEGLU: tile columns [0,64) = a, [64,128) = gate for output columns n0/2 + [0,64)
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        for (int c = half; c < 2; c += 2) {
           uint32_t ra[32], rg[32];
           tmem_ld_32x32(t_row + c * 32, ra);
           tmem_ld_32x32(t_row + 64 + c * 32, rg);
           tmem_ld_wait();
-          float v[32];
+          float v[32], gg[32];
+          epi_affine32<LNF>(ra, s_bias + c * 32, s_cs + c * 32, ln_rstd, -ln_mr, v);
+          epi_affine32<LNF>(rg, s_bias + 64 + c * 32, s_cs + 64 + c * 32, ln_rstd, -ln_mr, gg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(ra[j]) + s_bias[c * 32 + j];
-            const float g = __uint_as_float(rg[j]) + s_bias[64 + c * 32 + j];
-            v[j] = a * gelu_erf(g);
-          }
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gg[j]);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
@@ -302,8 +355,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
       const int rsub = lane >> 2, g = lane & 3;
       const int mrow0 = m0 + q * 32;
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f}, rsq[4] = {0.f, 0.f, 0.f, 0.f};      // per-row partials (rowstats_out)
 #pragma unroll 1
-      for (int c = 0; c < NOUT / 32; ++c) {
+      for (int c = half; c < NOUT / 32; c += 2) {
         const int n = nbase + c * 32 + g * 8;
         const int nvalid = ncols - n;
         uint4 res[4];
@@ -343,10 +397,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+          if (p.rowstats_out) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvalid) { rsum[u] += v[j]; rsq[u] = fmaf(v[j], v[j], rsq[u]); }
+          }
         }
         if (p.stats) {      // uniform across the CTA; rows of one warp lie in one image (stats_rows % 32 == 0)
           const int bimg = mrow0 / p.stats_rows;
           stats_commit(ssum, ssq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
+        }
+      }
+      if (p.rowstats_out) {
+        // fold the four column-group lanes of each row, then one fixed-point atomic pair per row and N tile
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          rsum[u] += __shfl_xor_sync(0xffffffffu, rsum[u], 1); rsq[u] += __shfl_xor_sync(0xffffffffu, rsq[u], 1);
+          rsum[u] += __shfl_xor_sync(0xffffffffu, rsum[u], 2); rsq[u] += __shfl_xor_sync(0xffffffffu, rsq[u], 2);
+          const int m = mrow0 + u * 8 + rsub;
+          if (g == 0 && m < p.M) {
+            atomicAdd(p.rowstats_out + 2 * (size_t)m, (unsigned long long)__float2ll_rn(rsum[u] * STATS_SCALE));
+            atomicAdd(p.rowstats_out + 2 * (size_t)m + 1, (unsigned long long)__float2ll_rn(rsq[u] * STATS_SCALE));
+          }
         }
       }
     }
@@ -359,12 +431,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, bool CONV, bool GEGLU>
+template <int BN, bool CONV, bool GEGLU, bool LNF = false>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -373,7 +445,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     attr_done = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM));
-  gemm_tc_kernel<BN, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
+  gemm_tc_kernel<BN, CONV, GEGLU, LNF><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -392,14 +464,14 @@ struct Tc2Cfg {
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns between accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int EPI_PITCH = 36;                                          // floats per staged row (32 + pad)
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+  static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;
   static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_EPI + EPI_BYTES;                          // 2 x BN floats
-  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
+  static constexpr int OFF_BAR = OFF_BIAS + 4 * BN * 4;                   // bias + folded-LN column sums, double-buffered
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
-template <int BN, int STAGES, bool CONV, bool GEGLU>
+template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
@@ -419,7 +491,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -490,12 +562,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..5), overlapped with the next tile's main loop =====================
-    const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + (size_t)q * 32 * Cfg::EPI_PITCH;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::OFF_EPI) + (size_t)(warp - 2) * 32 * Cfg::EPI_PITCH;
     const int ncols = GEGLU ? (p.N >> 1) : p.N;
     const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
     const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     uint32_t it = 0;
+    longlong2 ln_raw = make_longlong2(0, 0);
+    if (LNF) ln_raw = ln_row_load(p, (blockIdx.x / num_n) * TC_BM + q * 32 + lane);    // first tile's row statistics
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
       const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
@@ -503,34 +577,44 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // this tile's bias slice (+ the row vector when the whole tile shares one) -> smem
       const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
       float* sb = s_bias + buf * BN;
+      float* scs = s_bias + 2 * BN + buf * BN;
       {
         const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
-        for (int j = threadIdx.x - 64; j < BN; j += 128) {
+        for (int j = threadIdx.x - 64; j < BN; j += 32 * TC_EPI_WARPS) {
           const int n = n0 + j;
-          float bv = 0.f;
+          float bv = 0.f, cs = 0.f;
           if (n < p.N) {
             if (p.bias) bv = __ldg(p.bias + n);
             if (rv0) bv += __ldg(rv0 + n);
+            if (p.ln_colsum) cs = __ldg(p.ln_colsum + n);
           }
           sb[j] = bv;
+          scs[j] = cs;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+      }
+      float ln_rstd = 1.f, ln_mr = 0.f;
+      if (LNF) {
+        ln_row_finish(p, ln_raw, ln_rstd, ln_mr);
+        // the next tile's statistics travel while this tile drains
+        const int tn = t + gridDim.x;
+        if (tn < num_tiles) ln_raw = ln_row_load(p, (tn / num_n) * TC_BM + q * 32 + lane);
       }
       mbar_wait(&tfull[buf], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       constexpr int NCHUNK = GEGLU ? 2 : BN / 32;
+      const int c_last = half + 2 * ((NCHUNK - 1 - half) / 2);      // this warp's last chunk
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = half; c < NCHUNK; c += 2) {
         // ---- TMEM -> registers -> (+bias, activation | GEGLU gate) -> per-warp fp32 staging [32 rows][32 cols]
         float v[32];
         if (!GEGLU) {
           uint32_t r[32];
           tmem_ld_32x32(t_row + c * 32, r);
           tmem_ld_wait();
-          if (c == NCHUNK - 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); }     // accumulator fully read
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + sb[c * 32 + j];
+          if (c == c_last) { tc_fence_before(); mbar_arrive(&tempty[buf]); }     // this warp is done with the accumulator
+          epi_affine32<LNF>(r, sb + c * 32, scs + c * 32, ln_rstd, -ln_mr, v);
           if (p.rowvec && !rv_shared) {
             const int m = m0 + q * 32 + lane;
             if (m < p.M) {
@@ -541,20 +625,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (p.act != C2D_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
           }
         } else {
           uint32_t ra[32], rg[32];
           tmem_ld_32x32(t_row + c * 32, ra);
           tmem_ld_32x32(t_row + 64 + c * 32, rg);
           tmem_ld_wait();
-          if (c == NCHUNK - 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); }
+          if (c == c_last) { tc_fence_before(); mbar_arrive(&tempty[buf]); }
+          float gg[32];
+          epi_affine32<LNF>(ra, sb + c * 32, scs + c * 32, ln_rstd, -ln_mr, v);
+          epi_affine32<LNF>(rg, sb + 64 + c * 32, scs + 64 + c * 32, ln_rstd, -ln_mr, gg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(ra[j]) + sb[c * 32 + j];
-            const float g = __uint_as_float(rg[j]) + sb[64 + c * 32 + j];
-            v[j] = a * gelu_erf(g);
-          }
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gg[j]);
         }
         float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
 #pragma unroll
@@ -619,13 +702,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, int STAGES, bool CONV, bool GEGLU>
+template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF = false>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = Tc2Cfg<BN, STAGES>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "persistent GEMM smem");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -636,7 +719,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   const int num_n = ceil_div(p.N, BN);
   const int num_tiles = num_n * ceil_div(p.M, TC_BM);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_tiles, num_n);
+  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_tiles, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -657,7 +740,7 @@ struct Tc3Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int EPI_PITCH = 36;                                          // floats per staged row (32 + pad)
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                      // aliases pipeline stage 0
+  static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;           // aliases the pipeline stages
   static constexpr int OFF_BIAS = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -665,7 +748,7 @@ struct Tc3Cfg {
 };
 
 template <int BN, int STAGES, bool CONV, bool GEGLU>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 2)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_n) {
   using Cfg = Tc3Cfg<BN, STAGES>;
@@ -752,8 +835,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (warps 2..5 of both CTAs) =====================
-    const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem) + (size_t)q * 32 * Cfg::EPI_PITCH;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * Cfg::EPI_PITCH;
     const int ncols = GEGLU ? (p.N >> 1) : p.N;
     const int nbase = GEGLU ? (n0 >> 1) : n0;
     const bool vec_y = (p.ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
@@ -761,7 +844,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
     {
       const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
-      for (int j = threadIdx.x - 64; j < BN; j += 128) {
+      for (int j = threadIdx.x - 64; j < BN; j += 32 * TC_EPI_WARPS) {
         const int n = n0 + j;
         float bv = 0.f;
         if (n < p.N) {
@@ -770,14 +853,14 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         s_bias[j] = bv;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
     }
     mbar_wait(tmem_full, 0);      // all MMAs retired: the pipeline smem of BOTH CTAs is idle (staging aliases stage 0)
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int NCHUNK = GEGLU ? BN / 64 : BN / 32;
 #pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
+    for (int c = half; c < NCHUNK; c += 2) {
       // ---- TMEM -> registers -> (+bias, activation | GEGLU gate) -> per-warp fp32 staging [32 rows][32 cols]
       float v[32];
       if (!GEGLU) {
@@ -796,7 +879,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.act != C2D_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
         }
       } else {
         // accumulator columns: 128-column groups of [a (64) | gate (64)]; output chunk c covers 32 outputs
@@ -809,7 +892,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < 32; ++j) {
           const float a = __uint_as_float(ra[j]) + s_bias[grp * 128 + sub * 32 + j];
           const float g = __uint_as_float(rg[j]) + s_bias[grp * 128 + 64 + sub * 32 + j];
-          v[j] = a * gelu_erf(g);
+          v[j] = a * gelu_fast(g);
         }
       }
       float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
@@ -955,9 +1038,11 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   if (ex && ex->stats)
     C2D_REQUIRE(!geglu && ex->stats_rows > 0 && ex->stats_rows % 32 == 0 && M % ex->stats_rows == 0,
                 "linear_tc: channel statistics need rows-per-image %% 32 == 0 (M=%d stats_rows=%d)", M, ex->stats_rows);
-  const bool pairk = use_pair();
+  const bool lnx = ex && (ex->ln_stats || ex->rowstats_out);      // only the single-CTA kernels carry these epilogues
+  const bool pairk = use_pair() && !lnx;
+  const bool ln_or_rs = lnx;       // these epilogues exist in the BN = 160 / 128 single-CTA kernels only
   const int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                       : (geglu ? 128 : (use_persistent(geglu) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+                       : (geglu ? 128 : ((use_persistent(geglu) && !ln_or_rs) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
   CUtensorMap tmA, tmA2, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
@@ -991,17 +1076,28 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   p.kb_split = cat ? K1 / TC_BK : p.num_k_blocks;
   p.stats = ex ? reinterpret_cast<unsigned long long*>(ex->stats) : nullptr;
   p.stats_rows = ex && ex->stats ? ex->stats_rows : 1;
+  if (ex && ex->ln_stats) {
+    C2D_REQUIRE(ex->ln_colsum && !rowvec && act == C2D_ACT_NONE, "linear_tc: folded LayerNorm needs column sums, no row vector, no activation");
+    p.ln_stats = ex->ln_stats; p.ln_colsum = ex->ln_colsum; p.ln_invK = 1.0f / (float)K; p.ln_eps = ex->ln_eps;
+  }
+  p.rowstats_out = ex ? reinterpret_cast<unsigned long long*>(ex->rowstats_out) : nullptr;
   if (pairk) {
     if (geglu) return BN == 256 ? launch_tc3<256, 3, false, true>(tmA, tmA2, tmB, p, s) : launch_tc3<128, 4, false, true>(tmA, tmA2, tmB, p, s);
     if (BN == 256) return launch_tc3<256, 3, false, false>(tmA, tmA2, tmB, p, s);
     if (BN == 160) return launch_tc3<160, 4, false, false>(tmA, tmA2, tmB, p, s);
     return launch_tc3<128, 4, false, false>(tmA, tmA2, tmB, p, s);
   }
-  if (use_persistent(geglu)) {
-    if (geglu) return launch_tc2<128, 6, false, true>(tmA, tmA2, tmB, p, s);
+  const bool lnf = p.ln_stats != nullptr;
+  if (geglu && lnf) return launch_tc2<128, 5, false, true, true>(tmA, tmA2, tmB, p, s);      // folded-LN GEGLU: persistent only
+  if (lnf) {
+    if (BN == 160) return launch_tc<160, false, false, true>(tmA, tmA2, tmB, p, s);
+    return launch_tc<128, false, false, true>(tmA, tmA2, tmB, p, s);
+  }
+  if (use_persistent(geglu) && !(ex && ex->rowstats_out)) {
+    if (geglu) return launch_tc2<128, 5, false, true>(tmA, tmA2, tmB, p, s);
     if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmA2, tmB, p, s);
-    if (BN == 64) return launch_tc2<64, 8, false, false>(tmA, tmA2, tmB, p, s);
-    return launch_tc2<128, 6, false, false>(tmA, tmA2, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 7, false, false>(tmA, tmA2, tmB, p, s);
+    return launch_tc2<128, 5, false, false>(tmA, tmA2, tmB, p, s);
   }
   if (geglu) return launch_tc<128, false, true>(tmA, tmA2, tmB, p, s);
   if (BN == 160) return launch_tc<160, false, false>(tmA, tmA2, tmB, p, s);
@@ -1063,8 +1159,8 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   }
   if (gemm_mode() == 2) {
     if (BN == 160) return launch_tc2<160, 5, true, false>(tmA, tmA, tmB, p, s);
-    if (BN == 64) return launch_tc2<64, 8, true, false>(tmA, tmA, tmB, p, s);
-    return launch_tc2<128, 6, true, false>(tmA, tmA, tmB, p, s);
+    if (BN == 64) return launch_tc2<64, 7, true, false>(tmA, tmA, tmB, p, s);
+    return launch_tc2<128, 5, true, false>(tmA, tmA, tmB, p, s);
   }
   if (BN == 160) return launch_tc<160, true, false>(tmA, tmA, tmB, p, s);
   return launch_tc<128, true, false>(tmA, tmA, tmB, p, s);

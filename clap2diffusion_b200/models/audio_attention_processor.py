@@ -100,18 +100,26 @@ class AudioAttnProcessor(nn.Module):
         return ops.linear(ehs, self._kv_weight(attn, ehs.dtype))
 
     # ---- per-step part -------------------------------------------------------------------------
+    supports_ln_fold = True
+
     def attend(self, attn, hidden_states: torch.Tensor, kv: torch.Tensor, residual: Optional[torch.Tensor] = None,
-               scale: float = 1.0) -> torch.Tensor:
-        """to_q -> softmax(q k^T d^-1/2) v -> to_out[0] (+ residual).  hidden_states [B,N,C]."""
+               scale: float = 1.0, ln_stats: Optional[torch.Tensor] = None,
+               row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """to_q -> softmax(q k^T d^-1/2) v -> to_out[0] (+ residual).  hidden_states [B,N,C].
+        ln_stats: the engine's LayerNorm-free mode -- hidden_states is the un-normalised residual stream, norm2 is
+        folded into the to_q GEMM (attn.ln_q, prepared by SD15UNet); row_stats: statistics accumulator of the output."""
         dt = hidden_states.dtype
         c = self._cache
         C = kv.shape[-1] // 2
-        q = ops.linear(hidden_states, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
+        if ln_stats is not None:
+            q = ops.linear(hidden_states, None, ln=attn.ln_q, ln_stats=ln_stats)
+        else:
+            q = ops.linear(hidden_states, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
         d = C // attn.heads
         o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=float(getattr(attn, "scale", d ** -0.5)) * scale)
         out_lin = _to_out_linear(attn)
         bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
-        return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual)
+        return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual, row_stats=row_stats)
 
     # ---- diffusers processor protocol ----------------------------------------------------------
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,

@@ -106,11 +106,24 @@ def _rows(x: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------------
+class LNFold:
+    """LayerNorm folded into the next linear layer (pack_lnfold): gamma-scaled weight, its column sums, folded bias."""
+    __slots__ = ("w", "colsum", "bias", "eps")
+
+    def __init__(self, w, colsum, bias, eps):
+        self.w, self.colsum, self.bias, self.eps = w, colsum, bias, float(eps)
+
+
 def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_per_vec=1, out=None,
-           impl=IMPL_AUTO, x2=None, stats=None, stats_rows=0):
+           impl=IMPL_AUTO, x2=None, stats=None, stats_rows=0, row_stats=None, ln=None, ln_stats=None):
     """y = act([x | x2] @ w.T + bias + rowvec[row // rows_per_vec]) + residual.   w: [N, K] (nn.Linear layout).
     x2: optional second source concatenated along K (bf16 tcgen05 path).  stats: optional int64 [B, N, 2] channel
-    statistics accumulator (rows_per_image = stats_rows) filled by the epilogue for group_norm_apply."""
+    statistics accumulator (rows_per_image = stats_rows) filled by the epilogue for group_norm_apply.
+    row_stats: optional int64 [M, 2] per-row statistics accumulator of y (for a following folded LayerNorm).
+    ln / ln_stats: LNFold of the preceding LayerNorm and the int64 [M, 2] row statistics of x: computes
+    LayerNorm(x) @ W.T + b without a LayerNorm kernel (w / bias arguments are taken from `ln`)."""
+    if ln is not None:
+        w, bias = ln.w, ln.bias
     _dev(x)
     M, K1, ldx = _rows(x)
     K, ldx2 = K1, 0
@@ -129,30 +142,45 @@ def linear(x, w, bias=None, *, act=ACT_NONE, residual=None, rowvec=None, rows_pe
         Mr, Nr, ldr = _rows(residual)
         assert Mr == M and Nr == N and residual.dtype == x.dtype
     with _Timed(2.0 * M * N * K, _nb(w, residual) + (M * K + M * N) * x.element_size()):
-        if x2 is None and stats is None:
+        if x2 is None and stats is None and row_stats is None and ln is None:
             check(lib.c2d_linear(x.data_ptr(), w.data_ptr(), _ptr(_f32(bias, "bias")), _ptr(_f32(rowvec, "rowvec")),
                                  int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K, ldx, ldy, ldr, act, _dt(x),
                                  impl, _stream()), "linear")
         else:
             if stats is not None:
                 assert stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == (M // stats_rows) * N * 2
+            if row_stats is not None:
+                assert row_stats.dtype == torch.int64 and row_stats.is_contiguous() and row_stats.numel() == M * 2
+            if ln is not None:
+                assert ln_stats is not None and ln_stats.dtype == torch.int64 and ln_stats.numel() == M * 2
             check(lib.c2d_linear_ex(x.data_ptr(), _ptr(x2), K1, ldx2, w.data_ptr(), _ptr(_f32(bias, "bias")),
                                     _ptr(_f32(rowvec, "rowvec")), int(rows_per_vec), _ptr(residual), out.data_ptr(), M, N, K,
-                                    ldx, ldy, ldr, act, _ptr(stats), int(stats_rows), _dt(x), _stream()), "linear_ex")
+                                    ldx, ldy, ldr, act, _ptr(stats), int(stats_rows), _ptr(row_stats),
+                                    _ptr(ln_stats) if ln is not None else None,
+                                    _ptr(_f32(ln.colsum, "colsum")) if ln is not None else None,
+                                    ln.eps if ln is not None else 0.0, _dt(x), _stream()), "linear_ex")
     return out
 
 
-def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=IMPL_AUTO):
-    """Fused GEGLU projection; w_packed/bias_packed from pack_geglu()."""
+def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=IMPL_AUTO, ln=None, ln_stats=None):
+    """Fused GEGLU projection; w_packed/bias_packed from pack_geglu().  ln / ln_stats: folded LayerNorm (packed LNFold)."""
     _dev(x)
+    if ln is not None:
+        w_packed, bias_packed = ln.w, ln.bias
     M, K, ldx = _rows(x)
     assert ldx == K, "geglu_linear takes a dense x"
     F = w_packed.shape[0] // 2
     if out is None:
         out = torch.empty(*x.shape[:-1], F, device=x.device, dtype=x.dtype)
     with _Timed(4.0 * M * F * K, _nb(x, w_packed, out)):
-        check(lib.c2d_geglu_linear(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")), out.data_ptr(),
-                                   M, F, K, 1, _dt(x), impl, _stream()), "geglu_linear")
+        if ln is None:
+            check(lib.c2d_geglu_linear(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")), out.data_ptr(),
+                                       M, F, K, 1, _dt(x), impl, _stream()), "geglu_linear")
+        else:
+            assert ln_stats is not None and ln_stats.dtype == torch.int64 and ln_stats.numel() == M * 2
+            check(lib.c2d_geglu_linear_ex(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias_packed, "bias")),
+                                          ln_stats.data_ptr(), _f32(ln.colsum, "colsum").data_ptr(), ln.eps, out.data_ptr(),
+                                          M, F, K, _dt(x), _stream()), "geglu_linear_ex")
     return out
 
 
@@ -430,6 +458,22 @@ def pack_conv3x3(w, dtype):
     out = torch.empty(Cout, 3, 3, Cin, device=w.device, dtype=dtype)
     check(lib.c2d_pack_conv3x3(w.data_ptr(), out.data_ptr(), Cout, Cin, _dt(out), _stream()), "pack_conv3x3")
     return out
+
+
+def pack_lnfold(w, gamma, beta, bias, dtype, eps=1e-5, out_dtype=None):
+    """Fold LayerNorm(gamma, beta) into the linear layer (w [N,K] fp32, bias [N] fp32 or None) that follows it.
+    Returns an LNFold whose weight has dtype `out_dtype` (default `dtype`); column sums are taken over the
+    `dtype`-rounded (bf16) weights."""
+    _dev(w)
+    w = _f32(w, "w")
+    N, K = w.shape
+    wo = torch.empty(N, K, device=w.device, dtype=out_dtype or dtype)
+    cs = torch.empty(N, device=w.device, dtype=torch.float32)
+    bo = torch.empty(N, device=w.device, dtype=torch.float32)
+    check(lib.c2d_pack_lnfold(w.data_ptr(), _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                              _ptr(_f32(bias, "bias")), wo.data_ptr(), cs.data_ptr(), bo.data_ptr(), N, K, _dt(wo),
+                              _stream()), "pack_lnfold")
+    return LNFold(wo, cs, bo, eps)
 
 
 def pack_geglu(w, bias, dtype):

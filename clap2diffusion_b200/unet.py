@@ -67,11 +67,16 @@ class SelfAttnProcessor:
     Accepts and ignores cross_attention_kwargs such as ``audio`` (decision D5)."""
 
     def __call__(self, attn: AttentionSite, hidden_states, encoder_hidden_states=None, attention_mask=None,
-                 temb=None, scale: float = 1.0, residual=None, **kwargs):
+                 temb=None, scale: float = 1.0, residual=None, ln_stats=None, row_stats=None, **kwargs):
+        """ln_stats: hidden_states is the UN-normalised stream and norm1 is folded into the QKV GEMM (attn.ln_qkv);
+        row_stats: accumulator for the row statistics of the output (the next LayerNorm's input)."""
         C = attn.to_q.out_features
-        qkv = ops.linear(hidden_states, attn.wqkv)
+        if ln_stats is not None:
+            qkv = ops.linear(hidden_states, None, ln=attn.ln_qkv, ln_stats=ln_stats)
+        else:
+            qkv = ops.linear(hidden_states, attn.wqkv)
         o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], attn.heads, scale=attn.scale * scale)
-        return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=residual)
+        return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=residual, row_stats=row_stats)
 
 
 class CrossAttnProcessor:
@@ -80,11 +85,17 @@ class CrossAttnProcessor:
     def prepare(self, attn: AttentionSite, encoder_hidden_states, audio=None):
         return ops.linear(encoder_hidden_states, attn.wkv)
 
-    def attend(self, attn: AttentionSite, hidden_states, kv, residual=None, scale: float = 1.0):
+    supports_ln_fold = True
+
+    def attend(self, attn: AttentionSite, hidden_states, kv, residual=None, scale: float = 1.0, ln_stats=None,
+               row_stats=None):
         C = attn.to_q.out_features
-        q = ops.linear(hidden_states, attn.to_q.weight)
+        if ln_stats is not None:
+            q = ops.linear(hidden_states, None, ln=attn.ln_q, ln_stats=ln_stats)
+        else:
+            q = ops.linear(hidden_states, attn.to_q.weight)
         o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=attn.scale * scale)
-        return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=residual)
+        return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=residual, row_stats=row_stats)
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                  scale: float = 1.0, **kwargs):
@@ -117,6 +128,9 @@ class _StatsArena:
         self.buf = torch.zeros(capacity, device=device, dtype=torch.int64)
         self.off = 0
 
+    def take_rows(self, M: int) -> torch.Tensor:
+        return self.take(M, 1)
+
     def take(self, B: int, C: int) -> torch.Tensor:
         n = B * C * 2
         if self.off + n > self.buf.numel():
@@ -136,6 +150,7 @@ class SD15UNet:
         self.impl = impl
         self.fuse_geglu = dtype == torch.bfloat16
         self.fused_gn = dtype == torch.bfloat16       # producer-side GroupNorm statistics (tcgen05 epilogues)
+        self.fold_ln = dtype == torch.bfloat16        # norm1/2/3 folded into the QKV / to_q / GEGLU GEMMs
         self._gn_channels = 0
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
@@ -201,12 +216,24 @@ class SD15UNet:
             site = AttentionSite(f"{tb}.{a}", lins["to_q"], lins["to_k"], lins["to_v"], lins["to_out"])
             if a == "attn1":
                 site.wqkv = torch.cat([lins["to_q"].weight, lins["to_k"].weight, lins["to_v"].weight], 0).contiguous()
+                if self.fold_ln:
+                    w32 = torch.cat([self._dev32(f"{tb}.{a}.{p}.weight") for p in ("to_q", "to_k", "to_v")], 0).contiguous()
+                    site.ln_qkv = ops.pack_lnfold(w32, self.w[f"{tb}.norm1.weight"], self.w[f"{tb}.norm1.bias"], None, self.dtype)
             else:
                 site.wkv = torch.cat([lins["to_k"].weight, lins["to_v"].weight], 0).contiguous()
+                if self.fold_ln:
+                    site.ln_q = ops.pack_lnfold(self._dev32(f"{tb}.{a}.to_q.weight"), self.w[f"{tb}.norm2.weight"],
+                                                self.w[f"{tb}.norm2.bias"], None, self.dtype)
             self.sites[f"{tb}.{a}"] = site
         w, b = self._dev32(f"{tb}.ff.net.0.proj.weight"), self._dev32(f"{tb}.ff.net.0.proj.bias")
         if self.fuse_geglu:
             self.w[f"{tb}.ff.geglu.weight"], self.w[f"{tb}.ff.geglu.bias"] = ops.pack_geglu(w, b, self.dtype)
+            if self.fold_ln:
+                f = ops.pack_lnfold(w, self.w[f"{tb}.norm3.weight"], self.w[f"{tb}.norm3.bias"], b, self.dtype,
+                                    out_dtype=torch.float32)
+                wp, bp = ops.pack_geglu(f.w, f.bias, self.dtype)
+                _, csp = ops.pack_geglu(f.w, f.colsum, self.dtype)
+                self.w[f"{tb}.ff.geglu_ln"] = ops.LNFold(wp, csp, bp, 1e-5)
         else:
             self.w[f"{tb}.ff.net.0.proj.weight"] = w if self.dtype == torch.float32 else ops.cast(w, self.dtype)
             self.w[f"{tb}.ff.net.0.proj.bias"] = b
@@ -352,18 +379,32 @@ class SD15UNet:
             h = ops.group_norm_apply(res, xs, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], GROUPS, 1e-6, False)
         else:
             h = ops.group_norm(res, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], GROUPS, 1e-6, False)
+        s1, s2 = self.sites[f"{tb}.attn1"], self.sites[f"{tb}.attn2"]
+        cached = kv.get(f"{tb}.attn2") if kv is not None else None
+        if (ar is not None and self.fold_ln and isinstance(s1.processor, SelfAttnProcessor) and cached is not None
+                and getattr(s2.processor, "supports_ln_fold", False)):
+            # LayerNorm-free block: every GEMM that writes the residual stream also accumulates its row statistics,
+            # every GEMM that reads LayerNorm(stream) takes the raw stream + statistics (ops.linear(ln=...))
+            M = B * H * W
+            rs0, rs1, rs2 = ar.take_rows(M), ar.take_rows(M), ar.take_rows(M)
+            h = ops.linear(h, w[f"{name}.proj_in.weight"], w[f"{name}.proj_in.bias"], impl=self.impl, row_stats=rs0)
+            h = s1.processor(s1, h, residual=h, ln_stats=rs0, row_stats=rs1, **kw)
+            h = s2.processor.attend(s2, h, cached, residual=h, ln_stats=rs1, row_stats=rs2)
+            g = ops.geglu_linear(h, None, None, ln=w[f"{tb}.ff.geglu_ln"], ln_stats=rs2)
+            h = ops.linear(g, w[f"{tb}.ff.net.2.weight"], w[f"{tb}.ff.net.2.bias"], residual=h, impl=self.impl)
+            so = ar.take(B, C)
+            out = ops.linear(h, w[f"{name}.proj_out.weight"], w[f"{name}.proj_out.bias"], residual=res, impl=self.impl,
+                             stats=so, stats_rows=H * W)
+            return out.view(B, H, W, C), so
         h = ops.linear(h, w[f"{name}.proj_in.weight"], w[f"{name}.proj_in.bias"], impl=self.impl)
         # attn1
-        s1 = self.sites[f"{tb}.attn1"]
         n1 = ops.layer_norm(h, w[f"{tb}.norm1.weight"], w[f"{tb}.norm1.bias"])
         if isinstance(s1.processor, SelfAttnProcessor):
             h = s1.processor(s1, n1, residual=h, **kw)
         else:
             h = ops.add(h, s1.processor(s1, n1, **kw))
         # attn2
-        s2 = self.sites[f"{tb}.attn2"]
         n2 = ops.layer_norm(h, w[f"{tb}.norm2.weight"], w[f"{tb}.norm2.bias"])
-        cached = kv.get(f"{tb}.attn2") if kv is not None else None
         if cached is not None and hasattr(s2.processor, "attend"):
             h = s2.processor.attend(s2, n2, cached, residual=h)
         else:
@@ -387,7 +428,13 @@ class SD15UNet:
         w, kw = self.w, (cross_attention_kwargs or {})
         ehs = encoder_hidden_states
         B = x.shape[0]
-        ar = _StatsArena(x.device, 2 * B * self._gn_channels) if self.fused_gn else None
+        ar = None
+        if self.fused_gn:
+            # channel statistics of every GroupNorm input + row statistics of the three LayerNorm inputs of the
+            # 5 / 5 / 5 / 1 transformer blocks at the four resolutions
+            H0, W0 = x.shape[1], x.shape[2]
+            rows = sum(n * (max(H0 >> l, 1) * max(W0 >> l, 1)) for l, n in enumerate((5, 5, 5, 1)))
+            ar = _StatsArena(x.device, 2 * B * self._gn_channels + 2 * 3 * B * rows)
         h = ops.conv3x3(x, w["conv_in.weight"], w["conv_in.bias"], impl=self.impl)
         hs = ops.channel_stats(h, ar.take(B, h.shape[-1])) if ar is not None else None
         if taps is not None:

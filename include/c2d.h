@@ -78,17 +78,31 @@ int c2d_group_norm(const void* x, const void* x2, const float* gamma, const floa
                    double* stats_ws, int B, int HW, int C1, int C2, int groups, float eps, int silu, int dtype,
                    void* stream);
 
-/* ---- tcgen05 (bf16) GEMM / convolution with the two optional extras of the product path:
+/* ---- tcgen05 GEMM / convolution with the optional extras of the product path (bf16 only: C2D_ERR_ARG for fp32;
+ *  same arithmetic as c2d_linear / c2d_conv3x3 otherwise):
  *  (1) A = [x | x2] concatenated along K (first K1 columns from x, K1 % 64 == 0): the UNet's skip concatenation
  *      `torch.cat([h, skip], 1)` feeding conv_shortcut is never materialised;
  *  (2) chan_stats != NULL: the epilogue also accumulates per-channel (sum, sum of squares) of y into
  *      chan_stats[M / stats_rows][N][2], 2^20 fixed-point 64-bit integers (caller zero-initialises), which
  *      c2d_group_norm_apply consumes -- the GroupNorm statistics pass over y disappears.
- *  Same arithmetic as c2d_linear / c2d_conv3x3 otherwise.  bf16 only: fails with C2D_ERR_ARG for fp32. */
+ *  (3) row_stats_out != NULL: per-row (sum, sum of squares) of y in the same fixed-point format, [M][2]
+ *      (caller zero-initialises) -- the statistics a following LayerNorm needs;
+ *  (4) ln_row_stats != NULL: LayerNorm folded into THIS GEMM: x is the un-normalised activation whose row
+ *      statistics are ln_row_stats, w / ln_colsum / bias come from c2d_pack_lnfold, and the epilogue applies
+ *      y = rstd_m (acc - mean_m colsum_n) + bias_n.  BasicTransformerBlock's norm1/2/3 kernels disappear. */
 int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w, const float* bias,
                   const float* rowvec, int rows_per_vec, const void* residual, void* y, int M, int N, int K,
-                  int ldx, int ldy, int ldr, int act, long long* chan_stats, int stats_rows, int dtype,
-                  void* stream);
+                  int ldx, int ldy, int ldr, int act, long long* chan_stats, int stats_rows,
+                  long long* row_stats_out, const long long* ln_row_stats, const float* ln_colsum, float ln_eps,
+                  int dtype, void* stream);
+/* GEGLU projection (packed weights, see c2d_geglu_linear) with the optional folded LayerNorm of (4). */
+int c2d_geglu_linear_ex(const void* x, const void* w, const float* bias, const long long* ln_row_stats,
+                        const float* ln_colsum, float ln_eps, void* y, int M, int F, int K, int dtype,
+                        void* stream);
+/* Weight preparation for (4):  w_out[n][k] = w[n][k] gamma[k] (dtype),  colsum[n] = sum_k bf16(w_out[n][k]),
+ * bias_out[n] = bias[n] + sum_k beta[k] w[n][k].  w fp32 [N][K] (nn.Linear layout). */
+int c2d_pack_lnfold(const float* w, const float* gamma, const float* beta, const float* bias, void* w_out,
+                    float* colsum, float* bias_out, int N, int K, int dtype, void* stream);
 int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual,
                    void* y, int B, int H, int W, int Cin, int Cout, int stride, long long* chan_stats, int dtype,
                    void* stream);

@@ -376,3 +376,43 @@ def test_errors_are_loud():
         ops.linear(x, rnd(8, 8), impl=ops.IMPL_TCGEN05)
     with pytest.raises(C2DError):
         ops.conv3x3(rnd(1, 7, 7, 8, dtype=BF16), rnd(8, 3, 3, 8, dtype=BF16), impl=ops.IMPL_TCGEN05)
+
+
+# ------------------------------------------------------------------ folded LayerNorm
+@pytest.mark.parametrize("M,C,N", [(4096, 320, 960), (1024, 640, 640), (256, 1280, 3840), (130, 320, 320)])
+def test_layernorm_folded_into_linear(M, C, N):
+    """row_stats from a producer GEMM + pack_lnfold weights: linear(ln=...) == linear(layer_norm(x))."""
+    x0, w0 = rnd(M, C, dtype=BF16), rnd(C, C, dtype=BF16, scale=C ** -0.5, seed=1)
+    r = rnd(M, C, dtype=BF16, seed=2) * 2 + 0.3
+    rs = torch.zeros(M * 2, device=DEV, dtype=torch.int64)
+    h = ops.linear(x0, w0, rnd(C, seed=3), residual=r, row_stats=rs)            # producer: stream + its row statistics
+    hf = h.double()
+    ref_st = torch.stack([hf.sum(1), (hf * hf).sum(1)], -1) * T.STATS_SCALE
+    assert float((rs.view(M, 2).double() - ref_st).abs().max() / ref_st.abs().max()) < 2e-3
+    gamma, beta = 1 + 0.2 * rnd(C, seed=4), 0.2 * rnd(C, seed=5)
+    w, b = rnd(N, C, scale=C ** -0.5, seed=6), rnd(N, seed=7)
+    ln = ops.pack_lnfold(w, gamma, beta, b, BF16)
+    y = ops.linear(h, None, ln=ln, ln_stats=rs)
+    ref = T.linear(T.layer_norm(h, gamma, beta), w.to(BF16), b)
+    assert rel(y, ref) < 1e-2
+    assert rel(y, ops.linear(ops.layer_norm(h, gamma, beta), w.to(BF16), b)) < 1e-2
+
+
+def test_layernorm_folded_into_geglu():
+    M, C, Fh = 2048, 320, 1280
+    h = rnd(M, C, dtype=BF16) * 1.5 + 0.2
+    rs = torch.zeros(M * 2, device=DEV, dtype=torch.int64)
+    ident = torch.eye(C, device=DEV, dtype=BF16)
+    h2 = ops.linear(h, ident, row_stats=rs)                                       # statistics of h itself
+    assert torch.equal(h2, h)
+    gamma, beta = 1 + 0.2 * rnd(C, seed=4), 0.2 * rnd(C, seed=5)
+    w, b = rnd(2 * Fh, C, scale=C ** -0.5, seed=6), rnd(2 * Fh, seed=7)
+    f = ops.pack_lnfold(w, gamma, beta, b, BF16, out_dtype=F32)
+    wp, bp = ops.pack_geglu(f.w, f.bias, BF16)
+    _, csp = ops.pack_geglu(f.w, f.colsum, BF16)
+    y = ops.geglu_linear(h, None, None, ln=ops.LNFold(wp, csp, bp, 1e-5), ln_stats=rs)
+    wq, bq = ops.pack_geglu(w, b, BF16)
+    ref = ops.geglu_linear(ops.layer_norm(h, gamma, beta), wq, bq)
+    assert rel(y, ref) < 1e-2
+    ref32 = T.geglu(T.linear(T.layer_norm(h, gamma, beta).float(), w, b))
+    assert rel(y, ref32) < 1e-2

@@ -176,9 +176,23 @@ def test_schedulers_match_oracle():
     assert np.allclose(plan.coef[:, 1], np.diff(np.asarray(sig)), rtol=1e-6)
 
 
-def _build_unet(W, dtype=torch.float32):
+def _build_unet(W, dtype=torch.float32, fused=False):
+    from clap2diffusion_b200 import unet as unet_mod
     from clap2diffusion_b200.unet import SD15UNet
-    unet = SD15UNet(W["unet"], device="cpu", dtype=dtype)
+    if fused:
+        # the bf16 product wiring (fused GroupNorm statistics, folded LayerNorms, fused GEGLU) in fp32 arithmetic
+        class _Fused(SD15UNet):
+            def __init__(self, *a, **k):
+                self._force = True
+                super().__init__(*a, **k)
+
+            def __setattr__(self, k, v):
+                if k in ("fused_gn", "fold_ln", "fuse_geglu") and getattr(self, "_force", False):
+                    v = True
+                object.__setattr__(self, k, v)
+        unet = _Fused(W["unet"], device="cpu", dtype=dtype)
+    else:
+        unet = SD15UNet(W["unet"], device="cpu", dtype=dtype)
     mgr = pproc.AudioProcessorManager(unet)
     mgr.setup_processors(mode="add")
     assert {k: len(v) for k, v in mgr.level_mapping.items()} == {"early": 4, "mid": 7, "late": 5}
@@ -212,12 +226,17 @@ def test_unet_fused_groupnorm_host_logic_vs_oracle(gold, W):
     g = gold("unet_16x16.npz")
     clap = _t(PL.clap_embedding(0))[None]
     with torch_ops.installed(), torch.no_grad():
-        unet, mgr = _build_unet(W)
-        unet.fused_gn = True
+        unet, mgr = _build_unet(W, fused=True)
         enc = phier.ImprovedHierarchicalAudioEncoder().eval()
         enc.load_state_dict(W["hier"])
         routed = enc.encode(clap, with_tokens77=False)["routed"]
         x = _t(PL.init_noise(5, 16, 16))[None]
+
+        def _no_norm(*a, **k):
+            raise AssertionError("the fused UNet path must not launch stand-alone LayerNorm / two-pass GroupNorm kernels")
+        from clap2diffusion_b200 import ops as _ops
+        _ops.layer_norm = _no_norm          # torch_ops.installed() restores both on exit
+        _ops.group_norm = _no_norm
         eps = unet(x, float(g["t"]), _t(PL.text_states("a beach"))[None],
                    cross_attention_kwargs=mgr.get_audio_kwargs(routed))
     assert rel_l2(eps, _t(g["eps"])) < 1e-4

@@ -29,11 +29,37 @@ def _add_stats(stats, y, B):
     stats.view(B, C, 2).add_(torch.round(st.double() * STATS_SCALE).to(torch.int64))
 
 
+def _add_row_stats(row_stats, y):
+    yy = y.float().reshape(-1, y.shape[-1])
+    st = torch.stack([yy.sum(1), (yy * yy).sum(1)], -1)
+    row_stats.view(-1, 2).add_(torch.round(st.double() * STATS_SCALE).to(torch.int64))
+
+
+def _ln_coeffs(ln_stats, K, eps):
+    st = ln_stats.view(-1, 2).double() / STATS_SCALE / K
+    mean = st[:, 0]
+    var = (st[:, 1] - mean * mean).clamp_min(0.0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    return mean.float(), rstd.float()
+
+
+def pack_lnfold(w, gamma, beta, bias, dtype, eps=1e-5, out_dtype=None):
+    wg = w * gamma[None, :]
+    cs = wg.to(torch.bfloat16).float().sum(1)
+    bo = (w * beta[None, :]).sum(1) + (bias if bias is not None else 0.0)
+    return real_ops.LNFold(wg.to(out_dtype or dtype).contiguous(), cs.contiguous(), bo.contiguous(), eps)
+
+
 def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1, out=None, impl=0, x2=None,
-           stats=None, stats_rows=0):
+           stats=None, stats_rows=0, row_stats=None, ln=None, ln_stats=None):
     if x2 is not None:
         x = torch.cat([x, x2], -1)
-    y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
+    if ln is not None:
+        mean, rstd = _ln_coeffs(ln_stats, x.shape[-1], ln.eps)
+        acc = F.linear(x.float(), ln.w.float()).reshape(-1, ln.w.shape[0])
+        y = (rstd[:, None] * (acc - mean[:, None] * ln.colsum[None, :]) + ln.bias[None, :]).reshape(*x.shape[:-1], -1)
+    else:
+        y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
     if rowvec is not None:
         M = y.numel() // y.shape[-1]
         idx = torch.arange(M, device=y.device) // rows_per_vec
@@ -43,6 +69,8 @@ def linear(x, w, bias=None, *, act=0, residual=None, rowvec=None, rows_per_vec=1
         y = y + residual.float().reshape(y.shape)
     if stats is not None:
         _add_stats(stats, y, (y.numel() // y.shape[-1]) // stats_rows)
+    if row_stats is not None:
+        _add_row_stats(row_stats, y)
     y = y.to(x.dtype)
     if out is not None:
         out.copy_(y.reshape(out.shape))
@@ -60,8 +88,13 @@ def pack_geglu(w, bias, dtype):
     return w[idx].to(dtype).contiguous(), (None if bias is None else bias[idx].float().contiguous())
 
 
-def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=0):
-    y = F.linear(x.float(), w_packed.float(), bias_packed)
+def geglu_linear(x, w_packed, bias_packed, *, out=None, impl=0, ln=None, ln_stats=None):
+    if ln is not None:
+        mean, rstd = _ln_coeffs(ln_stats, x.shape[-1], ln.eps)
+        acc = F.linear(x.float(), ln.w.float()).reshape(-1, ln.w.shape[0])
+        y = (rstd[:, None] * (acc - mean[:, None] * ln.colsum[None, :]) + ln.bias[None, :]).reshape(*x.shape[:-1], -1)
+    else:
+        y = F.linear(x.float(), w_packed.float(), bias_packed)
     M = y.numel() // y.shape[-1]
     y = y.reshape(M, -1, 2, 64)                     # blocks of (a[64], g[64])
     r = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(*x.shape[:-1], -1)
