@@ -137,12 +137,20 @@ def run_reference(args):
 # ======================================================================================================
 # our arm
 # ======================================================================================================
+def _unet_input(pipe, B2: int, dev):
+    """UNet input as the sampler feeds it: NHWC, 4 latent channels (+ 4 zero padding channels on the bf16 path)."""
+    c = 8 if getattr(pipe.unet, "conv_in_tc", False) else 4
+    x = torch.zeros(B2, LATENT, LATENT, c, device=dev, dtype=pipe.dtype)
+    x[..., :4] = torch.randn(B2, LATENT, LATENT, 4, device=dev).to(pipe.dtype)
+    return x
+
+
 def per_kernel_profile(pipe, m: int):
     """One eager (non-graph) UNet step at the benchmark batch with CUDA events around every libc2d launch."""
     from clap2diffusion_b200 import ops
     dev = pipe.device
     B2 = 2 * m
-    x = torch.randn(B2, LATENT, LATENT, 4, device=dev).to(pipe.dtype)
+    x = _unet_input(pipe, B2, dev)
     ctx = torch.randn(B2, 77, 768, device=dev).to(pipe.dtype)
     kv = pipe.unet.prepare_conditioning(ctx, None)
     table = pipe.unet.time_table([500.0])
@@ -169,7 +177,7 @@ def run_ncu_step(args):
     with contextlib.redirect_stdout(sys.stderr):
         pipe = AudioToImagePipeline.random_init(seed=0, device=dev, dtype=torch.bfloat16, with_vae=False)
     m = args.micro_batch
-    x = torch.randn(2 * m, LATENT, LATENT, 4, device=dev).to(torch.bfloat16)
+    x = _unet_input(pipe, 2 * m, dev)
     ctx = torch.randn(2 * m, 77, 768, device=dev).to(torch.bfloat16)
     kv = pipe.unet.prepare_conditioning(ctx, None)
     table = pipe.unet.time_table([500.0])

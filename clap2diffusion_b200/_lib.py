@@ -61,7 +61,7 @@ SIGNATURES = {
     "c2d_concat": [_p, _p, _p, _ll, _i, _i, _i, _p],
     "c2d_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _p],
-    "c2d_cfg_sched_step": [_p, _p, _p, _p, _i, _i, _f, _p, _i, _p],
+    "c2d_cfg_sched_step": [_p, _p, _p, _p, _i, _i, _f, _p, _i, _i, _p],
     "c2d_softmax_rows": [_p, _p, _i, _i, _f, _i, _p],
     "c2d_transpose": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_bcast_add": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

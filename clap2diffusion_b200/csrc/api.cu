@@ -64,7 +64,7 @@ int c2d_conv3x3(const void* x, const void* w, const float* bias, const float* ro
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, upsample2x);
   if (impl == C2D_IMPL_TCGEN05) {
-    C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, no fused upsample, pow2 output H/W, Cin %% 8 == 0, Cin >= 64");
+    C2D_REQUIRE(tc_ok, "conv3x3: tcgen05 path needs bf16, no fused upsample, pow2 output H/W, Cin %% 8 == 0");
     return conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, nullptr, s);
   }
   if (impl == C2D_IMPL_AUTO && tc_ok)

@@ -151,7 +151,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 template <typename T>
 __global__ void cfg_sched_kernel(const T* __restrict__ eps2, float* __restrict__ x, T* __restrict__ xin2,
                                  float* __restrict__ trace, int B, int HW, float g,
-                                 const float* __restrict__ coef) {
+                                 const float* __restrict__ coef, int cpitch) {
   const float ca = coef[0], cb = coef[1], in_scale = coef[2];
   long long n = (long long)B * 4 * HW;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,8 +169,11 @@ __global__ void cfg_sched_kernel(const T* __restrict__ eps2, float* __restrict__
   x[i] = xn;
   if (trace) trace[i] = xn;
   T xi = from_f<T>(xn * in_scale);
-  xin2[nh] = xi;
-  xin2[half + nh] = xi;
+  // the next UNet input may carry padded channels (cpitch = 8: conv_in then runs on the tensor cores); only the
+  // four real channels are written, the caller zero-initialises the padding once
+  const long long no = ((long long)b * HW + p) * cpitch + c;
+  xin2[no] = xi;
+  xin2[(long long)B * HW * cpitch + no] = xi;
 }
 
 // [Cout][Cin][3][3] fp32 -> [Cout][3][3][Cin] T
@@ -361,11 +364,12 @@ int c2d_nhwc_to_nchw(const void* x, float* y, int B, int C, int HW, int dtype, v
 }
 
 int c2d_cfg_sched_step(const void* eps2, float* x, void* xin2, float* trace, int B, int HW, float guidance,
-                       const float* coef, int dtype, void* stream) {
+                       const float* coef, int xin_cpitch, int dtype, void* stream) {
   C2D_REQUIRE(eps2 && x && xin2 && coef && B > 0 && HW > 0, "cfg_sched_step: bad args");
+  C2D_REQUIRE(xin_cpitch >= 4, "cfg_sched_step: xin2 channel pitch %d < 4", xin_cpitch);
   long long n = (long long)B * 4 * HW;
   DISPATCH_T(dtype, cfg_sched_kernel<T><<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)eps2, x, (T*)xin2, trace, B, HW, guidance, coef);)
+                        (const T*)eps2, x, (T*)xin2, trace, B, HW, guidance, coef, xin_cpitch);)
   return check_launch("cfg_sched_step");
 }
 

@@ -1110,14 +1110,14 @@ bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int
   if (up || (stride != 1 && stride != 2)) return false;
   if (stride == 2 && ((H & 1) || (W & 1))) return false;
   const int Ho = H / stride, Wo = W / stride;
-  return Cin % 8 == 0 && Cin >= 64 && Cout >= 1 && is_pow2(Wo) && is_pow2(Ho) && al16(x) && al16(w) &&
+  return Cin % 8 == 0 && Cin >= 8 && Cout >= 1 && is_pow2(Wo) && is_pow2(Ho) && al16(x) && al16(w) &&
          ((long long)Ho * Wo >= 128 || 128 % (Ho * Wo) == 0) && (stride == 1 || Wo <= 128);
 }
 
 int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
                int H, int W, int Cin, int Cout, int stride, long long* stats, cudaStream_t s) {
   C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
-              "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0, Cin >= 64 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+              "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
   const int Ho = H / stride, Wo = W / stride;
   const int bw = Wo < 128 ? Wo : 128;
   const int bh = (128 / bw) < Ho ? (128 / bw) : Ho;

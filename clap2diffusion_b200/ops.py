@@ -416,15 +416,16 @@ def nhwc_to_nchw(x, *, out=None):
 
 def cfg_sched_step(eps2, x, xin2, guidance: float, coef, trace=None):
     """In place: x <- ca*x + cb*(eps_u + g (eps_c - eps_u)); xin2 <- cat[x, x] * in_scale (NHWC, eps2.dtype).
-    coef: device fp32 tensor [3] = (ca, cb, in_scale)."""
+    coef: device fp32 tensor [3] = (ca, cb, in_scale).  xin2 may have 8 channels (4 real + 4 zero padding the caller
+    initialised): only the real ones are written."""
     _dev(eps2)
     B = x.shape[0]
     HW = x.shape[2] * x.shape[3]
     assert eps2.is_contiguous() and xin2.is_contiguous() and eps2.shape[0] == 2 * B and xin2.dtype == eps2.dtype
-    assert coef.is_cuda and coef.numel() >= 3
+    assert coef.is_cuda and coef.numel() >= 3 and eps2.shape[-1] == 4 and xin2.shape[-1] in (4, 8)
     check(lib.c2d_cfg_sched_step(eps2.data_ptr(), _f32(x, "x").data_ptr(), xin2.data_ptr(), _ptr(_f32(trace, "trace")),
-                                 B, HW, float(guidance), _f32(coef, "coef").data_ptr(), _dt(eps2), _stream()),
-          "cfg_sched_step")
+                                 B, HW, float(guidance), _f32(coef, "coef").data_ptr(), int(xin2.shape[-1]), _dt(eps2),
+                                 _stream()), "cfg_sched_step")
     return x
 
 

@@ -47,7 +47,8 @@ class Sampler:
     def _state(self, B: int, H: int, W: int, kv, guidance: float) -> dict:
         dev, dt = self.unet.device, self.unet.dtype
         return dict(x=torch.empty(B, 4, H, W, device=dev, dtype=torch.float32),
-                    xin2=torch.empty(2 * B, H, W, 4, device=dev, dtype=dt),
+                    # bf16: 4 real + 4 zero channels so that conv_in is a tcgen05 implicit GEMM (16-byte TMA rows)
+                    xin2=torch.zeros(2 * B, H, W, 8 if self.unet.conv_in_tc else 4, device=dev, dtype=dt),
                     temb_row=torch.empty(self.unet._temb_total, device=dev, dtype=torch.float32),
                     coef=torch.empty(3, device=dev, dtype=torch.float32), kv=kv, guidance=float(guidance), graph=None)
 

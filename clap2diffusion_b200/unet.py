@@ -151,6 +151,7 @@ class SD15UNet:
         self.fuse_geglu = dtype == torch.bfloat16
         self.fused_gn = dtype == torch.bfloat16       # producer-side GroupNorm statistics (tcgen05 epilogues)
         self.fold_ln = dtype == torch.bfloat16        # norm1/2/3 folded into the QKV / to_q / GEGLU GEMMs
+        self.conv_in_tc = dtype == torch.bfloat16     # conv_in on the tensor cores over a channel-padded (4 -> 8) input
         self._gn_channels = 0
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
@@ -245,6 +246,11 @@ class SD15UNet:
             self.w[f"{n}.weight"] = self._dev32(f"{n}.weight")
             self.w[f"{n}.bias"] = self._dev32(f"{n}.bias")
         self._conv("conv_in")
+        if self.conv_in_tc:
+            w4 = self._dev32("conv_in.weight")
+            w8 = torch.zeros(w4.shape[0], 8, 3, 3, device=self.device, dtype=torch.float32)
+            w8[:, :4].copy_(w4)
+            self.w["conv_in8.weight"] = ops.pack_conv3x3(w8, self.dtype)
         for i, blk in enumerate(self.down):
             for j, (cin, cout) in enumerate(blk["resnets"]):
                 self._pack_resnet(f"down_blocks.{i}.resnets.{j}", cin, cout)
@@ -424,7 +430,8 @@ class SD15UNet:
     def forward_nhwc(self, x: torch.Tensor, temb_row: torch.Tensor, kv: Optional[Dict[str, torch.Tensor]] = None,
                      encoder_hidden_states: Optional[torch.Tensor] = None,
                      cross_attention_kwargs: Optional[dict] = None, taps: Optional[dict] = None) -> torch.Tensor:
-        """x [B,H,W,4] (engine dtype), temb_row fp32 [sum(Cout)] (one row of time_table) -> eps [B,H,W,4]."""
+        """x [B,H,W,4] (or [B,H,W,8] with four zero padding channels, see conv_in_tc) in the engine dtype,
+        temb_row fp32 [sum(Cout)] (one row of time_table) -> eps [B,H,W,4]."""
         w, kw = self.w, (cross_attention_kwargs or {})
         ehs = encoder_hidden_states
         B = x.shape[0]
@@ -435,8 +442,12 @@ class SD15UNet:
             H0, W0 = x.shape[1], x.shape[2]
             rows = sum(n * (max(H0 >> l, 1) * max(W0 >> l, 1)) for l, n in enumerate((5, 5, 5, 1)))
             ar = _StatsArena(x.device, 2 * B * self._gn_channels + 2 * 3 * B * rows)
-        h = ops.conv3x3(x, w["conv_in.weight"], w["conv_in.bias"], impl=self.impl)
-        hs = ops.channel_stats(h, ar.take(B, h.shape[-1])) if ar is not None else None
+        if x.shape[-1] == 8:          # channel-padded input (sampler, bf16): tensor-core conv_in with fused statistics
+            hs = ar.take(B, BLOCK_OUT[0]) if ar is not None else None
+            h = ops.conv3x3(x, w["conv_in8.weight"], w["conv_in.bias"], impl=self.impl, stats=hs)
+        else:
+            h = ops.conv3x3(x, w["conv_in.weight"], w["conv_in.bias"], impl=self.impl)
+            hs = ops.channel_stats(h, ar.take(B, h.shape[-1])) if ar is not None else None
         if taps is not None:
             taps["conv_in"] = h
         skips = [(h, hs)]

@@ -161,9 +161,11 @@ int c2d_nhwc_to_nchw(const void* x, float* y, int B, int C, int HW, int dtype, v
  *                                                       Euler:       ca = 1, cb = sigma_next - sigma)
  *  then writes the next UNet input xin2 (dtype NHWC [2B][HW][4]) = cat[x, x] * in_scale
  *  (in_scale = 1 for DDIM, 1/sqrt(sigma_next^2+1) for Euler).  coef = DEVICE fp32 {ca, cb, in_scale} so one
- *  captured CUDA graph serves every step.  Optionally records x to trace (fp32). */
+ *  captured CUDA graph serves every step.  Optionally records x to trace (fp32).
+ *  xin_cpitch >= 4: channel pitch of xin2; with 8 the four real channels are followed by zero padding the caller
+ *  initialised once, which lets conv_in (Cin = 4) run as a tcgen05 implicit GEMM (16-byte TMA rows). */
 int c2d_cfg_sched_step(const void* eps2, float* x, void* xin2, float* trace, int B, int HW, float guidance,
-                       const float* coef, int dtype, void* stream);
+                       const float* coef, int xin_cpitch, int dtype, void* stream);
 
 /* row softmax y = softmax(x * scale) over the last dim of x[M][N]; batched transpose y[b][C][R] = x[b][R][C].
  * Used by the materialised attention route for head dims the flash kernels do not take

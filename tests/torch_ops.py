@@ -229,7 +229,7 @@ def cfg_sched_step(eps2, x, xin2, guidance, coef, trace=None):
     if trace is not None:
         trace.copy_(x)
     xi = (x * coef[2]).permute(0, 2, 3, 1).to(xin2.dtype)
-    xin2.copy_(torch.cat([xi, xi], 0).reshape(xin2.shape))
+    xin2[..., :4].copy_(torch.cat([xi, xi], 0).reshape(*xin2.shape[:-1], 4))
     return x
 
 
