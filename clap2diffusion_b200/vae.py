@@ -25,6 +25,7 @@ class VAEDecoder:
         self.device, self.dtype, self.impl = torch.device(device), dtype, impl
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
+        self.fused_gn = dtype == torch.bfloat16       # GroupNorm statistics from the producing tcgen05 epilogues
         self._pack()
         self._sd = None
 
@@ -78,23 +79,47 @@ class VAEDecoder:
         self._conv("decoder.conv_out")
 
     # ------------------------------------------------------------------ forward
-    def _res(self, p, x):
+    # Above this many pixels per image the epilogue statistics are not used: thousands of M tiles per image would
+    # all hit the same B x C x 2 accumulators (measured: the 256^2 / 512^2 convolutions lose more to atomic
+    # contention than the saved statistics pass is worth), so those levels keep the two-pass GroupNorm.
+    FUSED_GN_MAX_HW = 128 * 128
+
+    def _stats(self, B: int, C: int, hw: int = 0):
+        if not self.fused_gn or hw > self.FUSED_GN_MAX_HW:
+            return None
+        return torch.zeros(B * C * 2, device=self.device, dtype=torch.int64)
+
+    def _gn(self, x, xs, p, silu=True):
         w = self.w
-        h = ops.group_norm(x, w[f"{p}.norm1.weight"], w[f"{p}.norm1.bias"], GROUPS, EPS, True)
-        h = ops.conv3x3(h, w[f"{p}.conv1.weight"], w[f"{p}.conv1.bias"], impl=self.impl)
-        h = ops.group_norm(h, w[f"{p}.norm2.weight"], w[f"{p}.norm2.bias"], GROUPS, EPS, True)
+        if xs is None and self.fused_gn:      # high-resolution level: stand-alone statistics pass, same one-pass apply
+            B, C = x.shape[0], x.shape[-1]
+            xs = ops.channel_stats(x.view(B, -1, C), torch.zeros(B * C * 2, device=self.device, dtype=torch.int64))
+        if xs is not None:
+            return ops.group_norm_apply(x, xs, w[f"{p}.weight"], w[f"{p}.bias"], GROUPS, EPS, silu)
+        return ops.group_norm(x, w[f"{p}.weight"], w[f"{p}.bias"], GROUPS, EPS, silu)
+
+    def _res(self, p, x, xs):
+        """ResnetBlock2D; (x, xs) = activation and its channel statistics (None on the fp32 path); returns the same pair."""
+        w = self.w
+        B, cout = x.shape[0], w[f"{p}.conv1.weight"].shape[0]
+        h = self._gn(x, xs, f"{p}.norm1")
+        hw = x.shape[1] * x.shape[2]
+        s1 = self._stats(B, cout, hw)
+        h = ops.conv3x3(h, w[f"{p}.conv1.weight"], w[f"{p}.conv1.bias"], impl=self.impl, stats=s1)
+        h = self._gn(h, s1, f"{p}.norm2")
         sc = x
         if f"{p}.conv_shortcut.weight" in w:
             sc = ops.linear(x, w[f"{p}.conv_shortcut.weight"], w[f"{p}.conv_shortcut.bias"], impl=self.impl)
-        return ops.conv3x3(h, w[f"{p}.conv2.weight"], w[f"{p}.conv2.bias"], residual=sc, impl=self.impl)
+        so = self._stats(B, cout, hw)
+        return ops.conv3x3(h, w[f"{p}.conv2.weight"], w[f"{p}.conv2.bias"], residual=sc, impl=self.impl, stats=so), so
 
-    def _mid_attention(self, x):
+    def _mid_attention(self, x, xs):
         w = self.w
         a = "decoder.mid_block.attentions.0"
         B, H, W, C = x.shape
         N = H * W
         xf = x.view(B, N, C)
-        hn = ops.group_norm(xf, w[f"{a}.group_norm.weight"], w[f"{a}.group_norm.bias"], GROUPS, EPS, False)
+        hn = self._gn(xf, xs, f"{a}.group_norm", silu=False)
         qkv = ops.linear(hn, w[f"{a}.qkv.weight"], w[f"{a}.qkv.bias"], impl=self.impl)          # [B,N,3C]
         o = torch.empty(B, N, C, device=x.device, dtype=x.dtype)
         for b in range(B):           # single head, d = C = 512: materialised scores per image
@@ -103,28 +128,33 @@ class VAEDecoder:
             p = ops.softmax_rows(s, scale=C ** -0.5)
             vt = ops.transpose(v.contiguous().view(1, N, C)).view(C, N)                          # [C,N]
             ops.linear(p, vt, out=o[b], impl=self.impl)                                          # p v    [N,C]
-        out = ops.linear(o, w[f"{a}.to_out.0.weight"], w[f"{a}.to_out.0.bias"], residual=xf, impl=self.impl)
-        return out.view(B, H, W, C)
+        so = self._stats(B, C)
+        out = ops.linear(o, w[f"{a}.to_out.0.weight"], w[f"{a}.to_out.0.bias"], residual=xf, impl=self.impl,
+                         stats=so, stats_rows=N)
+        return out.view(B, H, W, C), so
 
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         """z fp32 NCHW [B,4,h,w] (scaled latents) -> image fp32 NCHW [B,3,8h,8w]."""
         w = self.w
         x = ops.nchw_to_nhwc(z.contiguous().float(), self.dtype)
+        B = x.shape[0]
         h = ops.linear(x, w["post_quant_conv.weight"], w["post_quant_conv.bias"], impl=self.impl)
         h = ops.conv3x3(h, w["decoder.conv_in.weight"], w["decoder.conv_in.bias"], impl=self.impl)
-        h = self._res("decoder.mid_block.resnets.0", h)
-        h = self._mid_attention(h)
-        h = self._res("decoder.mid_block.resnets.1", h)
+        hs = ops.channel_stats(h, self._stats(B, h.shape[-1])) if self.fused_gn else None
+        h, hs = self._res("decoder.mid_block.resnets.0", h, hs)
+        h, hs = self._mid_attention(h, hs)
+        h, hs = self._res("decoder.mid_block.resnets.1", h, hs)
         for i in range(4):
             for j in range(3):
-                h = self._res(f"decoder.up_blocks.{i}.resnets.{j}", h)
+                h, hs = self._res(f"decoder.up_blocks.{i}.resnets.{j}", h, hs)
             if i < 3:
                 n = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                if self.dtype == torch.bfloat16:
-                    h = ops.conv3x3(ops.upsample2x(h), w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl)
+                if self.dtype == torch.bfloat16 or self.fused_gn:
+                    hs = self._stats(B, w[f"{n}.weight"].shape[0], 4 * h.shape[1] * h.shape[2])
+                    h = ops.conv3x3(ops.upsample2x(h), w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl, stats=hs)
                 else:
                     h = ops.conv3x3(h, w[f"{n}.weight"], w[f"{n}.bias"], upsample=True, impl=self.impl)
-        h = ops.group_norm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], GROUPS, EPS, True)
+        h = self._gn(h, hs, "decoder.conv_norm_out")
         h = ops.conv3x3(h, w["decoder.conv_out.weight"], w["decoder.conv_out.bias"], impl=self.impl)
         return ops.nhwc_to_nchw(h)
 
