@@ -1006,9 +1006,11 @@ static int pick_bn_pair(int N) {
   if (N % 256 == 0) return 256;
   return 128;
 }
-static bool use_persistent(bool geglu = false) {
+// auto: persistent for the GEGLU projection and for the large-M linears whose main loop is long enough (K >= 640)
+// or whose output is wide enough (N >= 960) for the cross-tile prefetch to pay (measured: -5 .. -16 %)
+static bool use_persistent(bool geglu = false, int M = 0, int N = 0, int K = 0) {
   const int m = gemm_mode();
-  return m == 2 || (m == 0 && geglu);
+  return m == 2 || (m == 0 && (geglu || (M >= 16384 && (K >= 640 || N >= 960))));
 }
 
 // tile width: widest tile that still yields at least one tile per SM, else 64 (more CTAs, deeper ring)
@@ -1041,8 +1043,10 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool lnx = ex && (ex->ln_stats || ex->rowstats_out);      // only the single-CTA kernels carry these epilogues
   const bool pairk = use_pair() && !lnx;
   const bool ln_or_rs = lnx;       // these epilogues exist in the BN = 160 / 128 single-CTA kernels only
+  const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
+  (void)ln_or_rs;
   const int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                       : (geglu ? 128 : ((use_persistent(geglu) && !ln_or_rs) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+                       : (geglu ? 128 : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
   CUtensorMap tmA, tmA2, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
@@ -1090,10 +1094,14 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool lnf = p.ln_stats != nullptr;
   if (geglu && lnf) return launch_tc2<128, 5, false, true, true>(tmA, tmA2, tmB, p, s);      // folded-LN GEGLU: persistent only
   if (lnf) {
+    if (persist) {
+      if (BN == 160) return launch_tc2<160, 5, false, false, true>(tmA, tmA2, tmB, p, s);
+      return launch_tc2<128, 5, false, false, true>(tmA, tmA2, tmB, p, s);
+    }
     if (BN == 160) return launch_tc<160, false, false, true>(tmA, tmA2, tmB, p, s);
     return launch_tc<128, false, false, true>(tmA, tmA2, tmB, p, s);
   }
-  if (use_persistent(geglu) && !(ex && ex->rowstats_out)) {
+  if (persist) {
     if (geglu) return launch_tc2<128, 5, false, true>(tmA, tmA2, tmB, p, s);
     if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmA2, tmB, p, s);
     if (BN == 64) return launch_tc2<64, 7, false, false>(tmA, tmA2, tmB, p, s);
