@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libc2d.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_RELU = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 AUDIO_NONE, AUDIO_ADD, AUDIO_CONCAT = 0, 1, 2
 
@@ -69,6 +69,14 @@ SIGNATURES = {
     "c2d_hier_route": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "c2d_norm_scale": [_p, _p, _i, _i, _i, _f, _i, _i, _p],
     "c2d_legacy_combine": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "c2d_stft_frames": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_power_spectrum": [_p, _p, _ll, _i, _p],
+    "c2d_log_mel_affine": [_p, _p, _p, _p, _ll, _i, _f, _p],
+    "c2d_clap_patches": [_p, _p, _i, _i, _i, _i, _p],
+    "c2d_window_attention": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
+    "c2d_patch_merge": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_token_mean": [_p, _p, _i, _i, _i, _i, _p],
+    "c2d_l2_normalize": [_p, _p, _i, _i, _f, _p],
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }

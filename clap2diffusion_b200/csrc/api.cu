@@ -31,7 +31,7 @@ int c2d_linear(const void* x, const void* w, const float* bias, const float* row
   C2D_REQUIRE(x && w && y, "linear: null pointer");
   C2D_REQUIRE(M > 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, "linear: bad dims M=%d N=%d K=%d ldx=%d ldy=%d", M, N, K, ldx, ldy);
   C2D_REQUIRE(!residual || ldr >= N, "linear: bad residual stride %d", ldr);
-  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_SILU, "linear: bad act %d", act);
+  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_RELU, "linear: bad act %d", act);
   C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "linear: bad dtype %d", dtype);
   cudaStream_t s = (cudaStream_t)stream;
   bool tc_ok = dtype == C2D_BF16 && linear_tc_supported(x, w, M, N, K, ldx);
@@ -79,7 +79,7 @@ int c2d_linear_ex(const void* x, const void* x2, int K1, int ldx2, const void* w
   C2D_REQUIRE(x && w && y, "linear_ex: null pointer");
   C2D_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N, "linear_ex: bad dims M=%d N=%d K=%d ldy=%d", M, N, K, ldy);
   C2D_REQUIRE(!residual || ldr >= N, "linear_ex: bad residual stride %d", ldr);
-  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_SILU, "linear_ex: bad act %d", act);
+  C2D_REQUIRE(act >= C2D_ACT_NONE && act <= C2D_ACT_RELU, "linear_ex: bad act %d", act);
   C2D_REQUIRE(dtype == C2D_BF16, "linear_ex: the K-concatenated / statistics-producing GEMM exists on the tcgen05 (bf16) path only");
   C2D_REQUIRE(ldx >= (x2 ? K1 : K) && (!x2 || ldx2 >= K - K1), "linear_ex: bad row strides");
   C2D_REQUIRE(linear_tc_supported(x, w, M, N, K, ldx), "linear_ex: K %% 8 / ldx %% 8 / alignment");

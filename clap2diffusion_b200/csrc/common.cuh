@@ -102,12 +102,14 @@ __device__ __forceinline__ float silu_fast(float x) {
 __device__ __forceinline__ float apply_act_fast(float v, int act) {
   if (act == C2D_ACT_GELU) return gelu_fast(v);
   if (act == C2D_ACT_SILU) return silu_fast(v);
+  if (act == C2D_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == C2D_ACT_GELU) return gelu_erf(v);
   if (act == C2D_ACT_SILU) return silu_acc(v);
+  if (act == C2D_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 

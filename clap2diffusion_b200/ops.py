@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import lib, check
 
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = _lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_TCGEN05
-ACT_NONE, ACT_GELU, ACT_SILU = _lib.ACT_NONE, _lib.ACT_GELU, _lib.ACT_SILU
+ACT_NONE, ACT_GELU, ACT_SILU, ACT_RELU = _lib.ACT_NONE, _lib.ACT_GELU, _lib.ACT_SILU, _lib.ACT_RELU
 AUDIO_ADD, AUDIO_CONCAT = _lib.AUDIO_ADD, _lib.AUDIO_CONCAT
 
 # Set ONLY by tests/torch_ops.py while it swaps these functions for torch doubles (host-logic tests on a
@@ -550,4 +550,103 @@ def legacy_combine(fg, bg, amb, hierarchy_weights, D: int):
     check(lib.c2d_legacy_combine(fg.data_ptr(), bg.data_ptr(), amb.data_ptr(),
                                  _f32(hierarchy_weights, "hierarchy_weights").data_ptr(), out.data_ptr(), B, nf, nb,
                                  na, D, _dt(fg), _stream()), "legacy_combine")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CLAP HTSAT audio tower (log-mel front end, Swin window attention, patch merging, pooling)
+# ------------------------------------------------------------------------------------------------
+def stft_frames(wave, window, hop: int, n_frames: int, *, out=None):
+    """wave fp32 [B,T], window fp32 [n_fft] -> frames fp32 [B*n_frames, n_fft] (centered, reflect-padded, windowed)."""
+    _dev(wave)
+    B, T = wave.shape
+    n_fft = window.numel()
+    assert wave.is_contiguous() and window.is_contiguous()
+    if out is None:
+        out = torch.empty(B * n_frames, n_fft, device=wave.device, dtype=torch.float32)
+    check(lib.c2d_stft_frames(_f32(wave, "wave").data_ptr(), _f32(window, "window").data_ptr(), out.data_ptr(), B, T, n_fft,
+                              int(hop), int(n_frames), _stream()), "stft_frames")
+    return out
+
+
+def power_spectrum(dft, *, out=None):
+    """dft fp32 [M, 2*nb] = [re | im] -> fp32 [M, nb]."""
+    _dev(dft)
+    M, nb2 = dft.shape
+    assert dft.is_contiguous() and nb2 % 2 == 0
+    if out is None:
+        out = torch.empty(M, nb2 // 2, device=dft.device, dtype=torch.float32)
+    check(lib.c2d_power_spectrum(_f32(dft, "dft").data_ptr(), out.data_ptr(), M, nb2 // 2, _stream()), "power_spectrum")
+    return out
+
+
+def log_mel_affine(x, a, b, floor: float = 1e-10, *, out=None):
+    """10 log10(max(x, floor)) * a[f] + b[f] over x fp32 [M, F]."""
+    _dev(x)
+    M, Fm = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.c2d_log_mel_affine(_f32(x, "x").data_ptr(), _f32(a, "a").data_ptr(), _f32(b, "b").data_ptr(), out.data_ptr(),
+                                 M, Fm, float(floor), _stream()), "log_mel_affine")
+    return out
+
+
+def clap_patches(mel, dtype, *, out=None):
+    """mel fp32 [B, n_frames, 64] (BatchNorm applied) -> [B*4096, 16] patch vectors in `dtype`."""
+    _dev(mel)
+    B, n_frames, n_mel = mel.shape
+    assert mel.is_contiguous()
+    if out is None:
+        out = torch.empty(B * 4096, 16, device=mel.device, dtype=dtype)
+    check(lib.c2d_clap_patches(_f32(mel, "mel").data_ptr(), out.data_ptr(), B, n_frames, n_mel, _dt(out), _stream()),
+          "clap_patches")
+    return out
+
+
+def window_attention(qkv, bias, H: int, W: int, heads: int, shift: int, *, out=None):
+    """Swin 8x8 window attention: qkv [B, H*W, 3C], bias fp32 [heads, 64, 64] -> [B, H*W, C]."""
+    _dev(qkv)
+    B, N, C3 = qkv.shape
+    C = C3 // 3
+    assert qkv.is_contiguous() and N == H * W and bias.is_contiguous() and tuple(bias.shape) == (heads, 64, 64)
+    if out is None:
+        out = torch.empty(B, N, C, device=qkv.device, dtype=qkv.dtype)
+    d = C // heads
+    with _Timed(4.0 * B * N * 64 * C, _nb(qkv, out)):
+        check(lib.c2d_window_attention(qkv.data_ptr(), _f32(bias, "bias").data_ptr(), out.data_ptr(), B, H, W, C, heads,
+                                       int(shift), float(d ** -0.5), _dt(qkv), _stream()), "window_attention")
+    return out
+
+
+def patch_merge(x, H: int, W: int, *, out=None):
+    """x [B, H*W, C] -> [B, (H/2)*(W/2), 4C] (Swin patch-merging gather)."""
+    _dev(x)
+    B, N, C = x.shape
+    assert x.is_contiguous() and N == H * W
+    if out is None:
+        out = torch.empty(B, (H // 2) * (W // 2), 4 * C, device=x.device, dtype=x.dtype)
+    check(lib.c2d_patch_merge(x.data_ptr(), out.data_ptr(), B, H, W, C, _dt(x), _stream()), "patch_merge")
+    return out
+
+
+def token_mean(x, *, out=None):
+    """x [B, N, C] -> fp32 [B, C]."""
+    _dev(x)
+    B, N, C = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    check(lib.c2d_token_mean(x.data_ptr(), out.data_ptr(), B, N, C, _dt(x), _stream()), "token_mean")
+    return out
+
+
+def l2_normalize(x, eps: float = 1e-12, *, out=None):
+    """x fp32 [B, D] -> x / max(||x||, eps)."""
+    _dev(x)
+    B, D = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.c2d_l2_normalize(_f32(x, "x").data_ptr(), out.data_ptr(), B, D, float(eps), _stream()), "l2_normalize")
     return out

@@ -30,7 +30,7 @@ extern "C" {
 
 enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
 enum { C2D_F32 = 0, C2D_BF16 = 1 };
-enum { C2D_ACT_NONE = 0, C2D_ACT_GELU = 1, C2D_ACT_SILU = 2 };
+enum { C2D_ACT_NONE = 0, C2D_ACT_GELU = 1, C2D_ACT_SILU = 2, C2D_ACT_RELU = 3 };
 /* kernel family selector for the dense contractions */
 enum { C2D_IMPL_AUTO = 0, C2D_IMPL_SIMT = 1, C2D_IMPL_TCGEN05 = 2 };
 /* AudioAttnProcessor injection modes (models/audio_attention_processor.py:24) */
@@ -204,6 +204,30 @@ int c2d_pack_conv3x3(const float* w, void* out, int Cout, int Cin, int dtype, vo
  * bias [2F] -> interleaved the same way (fp32). */
 int c2d_pack_geglu(const float* w, const float* bias, void* w_out, float* bias_out, int F, int K, int dtype,
                    void* stream);
+
+/* ==== CLAP HTSAT audio tower (models/audio_encoder.py:164-174 -> HF ClapFeatureExtractor + ClapModel.get_audio_features) ====
+ * The dense layers use c2d_linear / c2d_layer_norm; these are the remaining pieces. */
+/* frames[(b*n_frames+f)][k] = wave[b][reflect(f*hop + k - n_fft/2)] * window[k]  (centered STFT framing, fp32) */
+int c2d_stft_frames(const float* wave, const float* window, float* frames, int B, int T, int n_fft, int hop, int n_frames,
+                    void* stream);
+/* dft [M][2*nb] = [re | im] (the fp32 GEMM of the frames against the constant DFT matrix) -> out [M][nb] = re^2 + im^2 */
+int c2d_power_spectrum(const float* dft, float* out, long long M, int nb, void* stream);
+/* y = 10 log10(max(x, floor)) * a[f] + b[f]: power_to_db fused with the eval-mode BatchNorm2d over mel bins */
+int c2d_log_mel_affine(const float* x, const float* a, const float* b, float* y, long long M, int F, float floor_value,
+                       void* stream);
+/* mel [B][n_frames][64] fp32 -> patches [B*4096][16] (dtype): bicubic n_frames -> 1024, 4-chunk fold to 256x256,
+ * 4x4/stride-4 patch gather (reshape_mel2img + the im2col of ClapAudioPatchEmbed.proj) */
+int c2d_clap_patches(const float* mel, void* patches, int B, int n_frames, int n_mel, int dtype, void* stream);
+/* Swin 8x8 window attention over a packed qkv [B][H*W][3C] with relative-position bias [heads][64][64], cyclic shift
+ * and shift mask folded into the addressing; out [B][H*W][C] in the un-shifted token order */
+int c2d_window_attention(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads, int shift,
+                         float scale, int dtype, void* stream);
+/* ClapAudioPatchMerging gather: x [B][H][W][C] -> out [B][H/2*W/2][4C] (order (0,0),(1,0),(0,1),(1,1)) */
+int c2d_patch_merge(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream);
+/* out[b][c] = mean over tokens of x [B][N][C] (fp32 result) */
+int c2d_token_mean(const void* x, float* out, int B, int N, int C, int dtype, void* stream);
+/* y = x / max(||x||_2, eps) per row of x [B][D] (fp32) */
+int c2d_l2_normalize(const float* x, float* y, int B, int D, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ kinds
   'emb'   free parameter (queries, offsets, positional tables): ``scale``*U(-sqrt3, sqrt3)
           (unit-variance uniform times scale)
   'scalar' gates/alpha: U(-0.5, 0.5) + ``shift``
+  'var'   positive running variance: ``scale`` * (1 + 0.3*U(-1,1))
 """
 from __future__ import annotations
 
@@ -57,6 +58,8 @@ def synth(p: P, seed: int) -> np.ndarray:
         u *= np.float32(p.scale * math.sqrt(3.0))
     elif p.kind == "scalar":
         u = np.float32(0.5) * u + np.float32(p.shift)
+    elif p.kind == "var":
+        u = np.float32(p.scale) * (np.float32(1.0) + np.float32(0.3) * u)
     else:
         raise ValueError(f"unknown kind {p.kind!r} for {p.name}")
     return np.asarray(u, dtype=np.float32).reshape(shape)   # (ascontiguousarray would turn 0-d into 1-d)

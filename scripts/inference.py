@@ -98,10 +98,21 @@ class AudioToImageInference:
         return a / (np.abs(a).max() + 1e-8)
 
     def extract_clap_embedding(self, audio):
-        """Deterministic unit-norm [1,512] stand-in keyed by the waveform (pretrained CLAP is unavailable;
-        the reference uses torch.randn(1, 512) here)."""
-        key = zlib.crc32(np.ascontiguousarray(audio, dtype=np.float32).tobytes())
-        return torch.from_numpy(synthetic.clap_embedding(key)[None]).to(self.device)
+        """Unit-norm [1,512] CLAP embedding of the clip from the GPU HTSAT tower (the reference has a
+        ``torch.randn(1, 512)`` placeholder here, :85-90).  Weights: ``clap_audio.pth`` (HF key layout) in the
+        checkpoint directory, else ``laion/clap-htsat-unfused`` from the local HF cache, else random init."""
+        if getattr(self, "clap_encoder", None) is None:
+            from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder
+            sd = self._load("clap_audio.pth")
+            if sd is not None:
+                self.clap_encoder = CLAPAudioEncoder(device=str(self.device), state_dict=sd, dtype=self.dtype)
+            else:
+                try:
+                    self.clap_encoder = CLAPAudioEncoder(device=str(self.device), dtype=self.dtype)
+                except RuntimeError:
+                    print("  no CLAP checkpoint available: random-initialised HTSAT tower")
+                    self.clap_encoder = CLAPAudioEncoder.random_init(seed=0, device=str(self.device), dtype=self.dtype)
+        return self.clap_encoder.encode_audio(np.asarray(audio, dtype=np.float32), 48000)
 
     def apply_normalization(self, audio_tokens, target_norm=60.0):
         """x * target / mean(||x||_2) (reference :92-99; batch-coupled mean, identical for batch 1)."""

@@ -1,0 +1,123 @@
+"""CLAP HTSAT audio tower on the GPU (-m gpu): kernels vs their torch restatements, the whole encoder vs the goldens
+produced by the UNMODIFIED Hugging Face CLAP (oracle/make_golden_clap.py).
+Tolerances: fp32 path rel-L2 <= 1e-4 on the embedding (summation order only), bf16 tower <= 2e-2 (12 Swin layers of
+bf16 activations; cosine similarity >= 0.9995)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import torch_ops as T
+from clap2diffusion_b200 import ops
+from clap2diffusion_b200.clap import ClapAudioTower
+from clap2diffusion_b200.synthetic import synthetic_audio
+from oracle import clap as C
+from oracle.weights import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def test_front_end_kernels():
+    wave = rnd(3, 48000, scale=0.3)
+    win = torch.hann_window(1024, periodic=True, device=DEV)
+    fr = ops.stft_frames(wave, win, 480, 101)
+    assert rel(fr, T.stft_frames(wave.cpu(), win.cpu(), 480, 101)) < 1e-6
+    dft = rnd(500, 1026, seed=1)
+    assert rel(ops.power_spectrum(dft), T.power_spectrum(dft.cpu())) < 1e-6
+    x = rnd(700, 64, seed=2).abs() * 1e-3
+    x[0, :8] = 0.0
+    a, b = rnd(64, seed=3), rnd(64, seed=4)
+    assert rel(ops.log_mel_affine(x, a, b), T.log_mel_affine(x.cpu(), a.cpu(), b.cpu())) < 1e-5
+    mel = rnd(2, 1001, 64, seed=5) * 10
+    assert rel(ops.clap_patches(mel, torch.float32), T.clap_patches(mel.cpu(), torch.float32)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,H,C,heads,shift", [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (3, 32, 192, 8, 4), (2, 16, 384, 16, 4),
+                                               (5, 8, 768, 32, 0)])
+def test_window_attention(B, H, C, heads, shift, dtype, tol):
+    qkv = rnd(B, H * H, 3 * C, seed=1).to(dtype)
+    bias = rnd(heads, 64, 64, seed=2, scale=0.5)
+    o = ops.window_attention(qkv, bias, H, H, heads, shift)
+    assert rel(o.float(), T.window_attention(qkv.cpu(), bias.cpu(), H, H, heads, shift).float()) < tol
+
+
+def test_merge_mean_normalize():
+    x = rnd(2, 32 * 32, 192, seed=1).to(torch.bfloat16)
+    assert torch.equal(ops.patch_merge(x, 32, 32).cpu(), T.patch_merge(x.cpu(), 32, 32))
+    assert rel(ops.token_mean(x), T.token_mean(x.cpu())) < 1e-5
+    z = rnd(7, 512, seed=2)
+    assert rel(ops.l2_normalize(z), T.l2_normalize(z.cpu())) < 1e-6
+    y = ops.linear(z, rnd(512, 512, seed=3, scale=0.05), rnd(512, seed=4), act=ops.ACT_RELU)
+    assert float(y.min()) >= 0.0
+
+
+@pytest.fixture(scope="module")
+def clap_setup():
+    g = np.load(os.path.join(GOLD, "clap_audio.npz"))
+    sd = {k: torch.from_numpy(v) for k, v in synth_state_dict(C.clap_audio_spec(), 4321).items()}
+    waves = np.stack([synthetic_audio(s) for s in (0, 1)])
+    waves[1] *= np.linspace(0.05, 1.0, waves.shape[1], dtype=np.float32)
+    return g, sd, torch.from_numpy(waves).to(DEV)
+
+
+def test_clap_encoder_fp32_vs_hf_golden(clap_setup):
+    g, sd, waves = clap_setup
+    tower = ClapAudioTower(sd, device=DEV, dtype=torch.float32, clip_chunk=1)
+    taps = {}
+    emb = tower.encode(waves, taps)
+    mel = (taps["mel_bn"] - tower.w["bn_b"]) / tower.w["bn_a"]
+    e_mel = rel(mel, torch.from_numpy(g["mel"][:, 0]))
+    e = {k: rel(taps[k][:, ::s], torch.from_numpy(g[k])) for k, s in (("patch_embed", 64), ("stage0", 64), ("stage2", 16))}
+    e_emb = rel(emb, torch.from_numpy(g["embedding"]))
+    print("fp32 CLAP: log-mel %.1e  patch_embed %.1e  stage0 %.1e  stage2 %.1e  embedding %.1e" %
+          (e_mel, e["patch_embed"], e["stage0"], e["stage2"], e_emb))
+    assert e_mel < 5e-5 and max(e.values()) < 1e-4 and e_emb < 1e-4
+    assert abs(float(emb.norm(dim=-1).mean()) - 1.0) < 1e-5
+
+
+def test_clap_encoder_bf16_vs_hf_golden(clap_setup):
+    g, sd, waves = clap_setup
+    tower = ClapAudioTower(sd, device=DEV, dtype=torch.bfloat16)
+    emb = tower.encode(waves)
+    ref = torch.from_numpy(g["embedding"]).to(DEV)
+    e = rel(emb, ref)
+    cos = float((emb * ref).sum(-1).min())
+    print("bf16 CLAP: embedding rel-L2 %.1e, min cosine %.5f" % (e, cos))
+    assert e < 2e-2 and cos > 0.9995
+    # batch invariance: a clip's embedding does not depend on its batch neighbours (data-parallel sharding by clip)
+    one = tower.encode(waves[1:2])
+    assert rel(one, emb[1:2]) < 1e-2
+
+
+def test_drop_in_audio_encoder(clap_setup):
+    """models.audio_encoder.CLAPAudioEncoder: reference call surface (list of numpy clips / tensors, preprocess_audio)."""
+    from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder, compute_audio_text_similarity
+    g, sd, waves = clap_setup
+    enc = CLAPAudioEncoder(device=DEV, state_dict=sd, dtype=torch.float32)
+    clips = [w for w in waves.cpu().numpy()]
+    emb = enc.encode_audio(clips, 48000)                      # list of clips
+    assert tuple(emb.shape) == (2, 512) and rel(emb, torch.from_numpy(g["embedding"])) < 1e-4
+    one = enc(clips[0][:240000])                              # short clip: zero-padded to 10 s like the reference
+    assert tuple(one.shape) == (1, 512) and abs(float(one.norm()) - 1.0) < 1e-5
+    stereo = np.stack([clips[1], clips[1]], axis=-1)          # [n, 2] -> mono by mean over the last axis (:110-111)
+    assert rel(enc.encode_audio(stereo, 48000), emb[1:2]) < 1e-5
+    assert rel(enc.encode_audio(waves), emb) < 1e-6           # device tensor fast path
+    sim = compute_audio_text_similarity(emb, emb)
+    assert tuple(sim.shape) == (2, 2) and abs(float(sim[0, 0]) - 1.0 / 0.07) < 1e-3
+    rnd_enc = CLAPAudioEncoder.random_init(seed=3, device=DEV)
+    z = rnd_enc.encode_audio(waves)
+    assert torch.isfinite(z).all() and abs(float(z.norm(dim=-1).mean()) - 1.0) < 1e-4

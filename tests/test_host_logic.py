@@ -284,3 +284,31 @@ def test_inference_cli_surface():
     cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "AudioToImageInference"][0]
     methods = {n.name for n in cls.body if isinstance(n, ast.FunctionDef)}
     assert {"load_models", "load_audio", "extract_clap_embedding", "apply_normalization", "generate", "batch_generate"} <= methods
+
+
+def test_clap_tower_host_logic_vs_oracle(gold):
+    """ClapAudioTower's packing (fused QKV, expanded relative-position bias, folded BatchNorm, DFT / mel matrices) and
+    launch sequence through the torch double == the oracle restatement == the HF goldens."""
+    from clap2diffusion_b200.clap import ClapAudioTower, param_shapes
+    from clap2diffusion_b200.synthetic import synthetic_audio
+    from oracle import clap as C
+    from oracle.weights import synth_state_dict
+    g = gold("clap_audio.npz")
+    spec = C.clap_audio_spec()
+    assert {p.name: tuple(p.shape) for p in spec} == param_shapes()
+    sd = {k: _t(v) for k, v in synth_state_dict(spec, 4321).items()}
+    waves = np.stack([synthetic_audio(s) for s in (0, 1)])
+    waves[1] *= np.linspace(0.05, 1.0, waves.shape[1], dtype=np.float32)
+    with torch_ops.installed(), torch.no_grad():
+        tower = ClapAudioTower(sd, device="cpu", dtype=torch.float32, clip_chunk=1)
+        taps = {}
+        emb = tower.encode(_t(waves), taps)
+    # front end vs the HF feature extractor (undo the folded BatchNorm)
+    mel = (taps["mel_bn"] - tower.w["bn_b"]) / tower.w["bn_a"]
+    assert rel_l2(mel, _t(g["mel"][:, 0])) < 2e-5
+    assert rel_l2(taps["patch_embed"][:, ::64], _t(g["patch_embed"])) < 1e-4
+    assert rel_l2(taps["stage0"][:, ::64], _t(g["stage0"])) < 1e-4
+    assert rel_l2(taps["stage2"][:, ::16], _t(g["stage2"])) < 1e-4
+    assert rel_l2(taps["pooled"], _t(g["pooled"])) < 1e-4
+    assert rel_l2(emb, _t(g["embedding"])) < 1e-4
+    assert int(g["n_params"]) == 28190872

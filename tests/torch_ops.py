@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from clap2diffusion_b200 import ops as real_ops
 
-ACT = {0: lambda v: v, 1: F.gelu, 2: F.silu}
+ACT = {0: lambda v: v, 1: F.gelu, 2: F.silu, 3: F.relu}
 
 
 STATS_SCALE = float(1 << 20)
@@ -273,6 +273,77 @@ def legacy_combine(fg, bg, amb, hierarchy_weights, D):
     B = fg.shape[0]
     w = torch.softmax(hierarchy_weights, 0)
     return torch.cat([fg.reshape(B, -1, D) * w[0], bg.reshape(B, -1, D) * w[1], amb.reshape(B, -1, D) * w[2]], 1)
+
+
+# ---- CLAP audio tower doubles -------------------------------------------------------------------------
+def stft_frames(wave, window, hop, n_frames, *, out=None):
+    n_fft = window.numel()
+    w = F.pad(wave[:, None, :], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    idx = torch.arange(n_frames)[:, None] * hop + torch.arange(n_fft)[None, :]
+    return (w[:, idx] * window[None, None, :]).reshape(-1, n_fft).contiguous()
+
+
+def power_spectrum(dft, *, out=None):
+    nb = dft.shape[1] // 2
+    return dft[:, :nb] ** 2 + dft[:, nb:] ** 2
+
+
+def log_mel_affine(x, a, b, floor=1e-10, *, out=None):
+    y = 10.0 * torch.log10(torch.clamp(x, min=floor)) * a[None, :] + b[None, :]
+    if out is not None:
+        out.copy_(y.reshape(out.shape))
+        return out
+    return y
+
+
+def clap_patches(mel, dtype, *, out=None):
+    B = mel.shape[0]
+    x = F.interpolate(mel[:, None], (1024, 64), mode="bicubic", align_corners=True)
+    img = x.reshape(B, 4, 256, 64).permute(0, 1, 3, 2).reshape(B, 256, 256)
+    p = img.reshape(B, 64, 4, 64, 4).permute(0, 1, 3, 2, 4).reshape(B * 4096, 16)
+    return p.contiguous().to(dtype)
+
+
+def window_attention(qkv, bias, H, W, heads, shift, *, out=None):
+    B, N, C3 = qkv.shape
+    C, d = C3 // 3, C3 // 3 // heads
+    t = qkv.float().view(B, H, W, C3)
+    if shift:
+        t = torch.roll(t, (-shift, -shift), (1, 2))
+    nh, nw = H // 8, W // 8
+    win = t.view(B, nh, 8, nw, 8, C3).permute(0, 1, 3, 2, 4, 5).reshape(-1, 64, C3)
+    q, k, v = (win[..., i * C:(i + 1) * C].reshape(-1, 64, heads, d).transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2) * d ** -0.5 + bias[None]
+    if shift:
+        img = torch.zeros(1, H, W, 1)
+        cnt = 0
+        for hs in (slice(0, -8), slice(-8, -shift), slice(-shift, None)):
+            for ws in (slice(0, -8), slice(-8, -shift), slice(-shift, None)):
+                img[:, hs, ws, :] = cnt
+                cnt += 1
+        m = img.view(1, nh, 8, nw, 8, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, 64)
+        dm = m[:, None, :] - m[:, :, None]
+        dm = torch.where(dm != 0, torch.full_like(dm, -100.0), torch.zeros_like(dm))
+        s = (s.view(B, nh * nw, heads, 64, 64) + dm[None, :, None]).view(-1, heads, 64, 64)
+    o = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(-1, 64, C)
+    o = o.view(B, nh, nw, 8, 8, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o.reshape(B, N, C).to(qkv.dtype)
+
+
+def patch_merge(x, H, W, *, out=None):
+    B, N, C = x.shape
+    t = x.view(B, H, W, C)
+    return torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1).reshape(B, -1, 4 * C).contiguous()
+
+
+def token_mean(x, *, out=None):
+    return x.float().mean(1)
+
+
+def l2_normalize(x, eps=1e-12, *, out=None):
+    return F.normalize(x, dim=-1, eps=eps)
 
 
 _NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and hasattr(real_ops, n)
