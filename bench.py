@@ -126,9 +126,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": img_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * (STEPS_DENOISE * step_s + dec_s), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "config 1/2: 1 image, 512x512, 50 DDIM steps, CFG 7.5, CPU oracle",
+        "config": {"workload": f"config 3 (prompt x seed sweep): micro-batch {args.micro_batch} images/rank/step (UNet batch "
+                               f"{2 * args.micro_batch} with CFG), 512x512, {STEPS_DENOISE} DDIM steps, CFG {GUIDANCE}, audio 'add' "
+                               f"processors on 16 attn2 sites, VAE decode",
+                   "micro_batch": args.micro_batch,
+                   "sample": sample,
                    "note": "reference repo ships no runnable UNet loop (scripts/inference.py fabricates the image); "
-                           "this is the oracle restatement of the intended path on host cores"},
+                           "this arm times the oracle restatement of the intended path on the host cores, one image at a "
+                           "time (images are independent, so images/s does not depend on the micro-batch)"},
         "cpu_baseline": {"value": img_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": img_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
