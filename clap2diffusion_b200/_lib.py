@@ -52,6 +52,10 @@ SIGNATURES = {
     "c2d_group_norm_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p],
     "c2d_layer_norm": [_p, _p, _p, _p, _i, _i, _f, _i, _p],
     "c2d_attention": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _f, _p, _i, _i, _p],
+    "c2d_xattn_supported": [_i, _i, _i, _i, _i, _i],
+    "c2d_xattn_packed_bytes": [_i, _i, _i, _i],
+    "c2d_xattn_pack_kv": [_p, _p, _ll, _ll, _i, _p, _p, _ll, _ll, _i, _p, _i, _i, _i, _i, _p],
+    "c2d_xattn_fwd": [_p, _ll, _p, _p, _p, _p, _f, _p, _i, _i, _f, _p, _ll, _i, _i, _i, _i, _f, _i, _p],
     "c2d_audio_context": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "c2d_timestep_embedding": [_p, _p, _i, _i, _p],
     "c2d_unary": [_p, _p, _ll, _i, _i, _i, _p],
@@ -80,7 +84,7 @@ SIGNATURES = {
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }
-_RESTYPES = {"c2d_last_error": C.c_char_p, "c2d_last_kernel": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
+_RESTYPES = {"c2d_xattn_packed_bytes": C.c_longlong, "c2d_last_error": C.c_char_p, "c2d_last_kernel": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = symbol missing from the .so

@@ -18,6 +18,12 @@ int attention_simt(const AttnParams&, int, int, cudaStream_t);
 int attention_small(const AttnParams&, int, int, cudaStream_t);
 bool attention_tc_supported(const AttnParams&, int B);
 int attention_tc(const AttnParams&, int B, cudaStream_t);
+bool xattn_tc_supported(int C, int heads, int Nq, int T, int T2);
+long long xattn_packed_bytes(int C, int heads, int T, int T2);
+int xattn_pack_kv(const void*, const void*, long long, long long, int, const void*, const void*, long long, long long, int, void*,
+                  int, int, int, cudaStream_t);
+int xattn_tc(const void*, long long, const void*, const float*, const long long*, const float*, float, const void*, int, int, float,
+             void*, long long, int, int, int, int, float, cudaStream_t);
 
 }  // namespace c2d
 
@@ -139,6 +145,38 @@ int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, i
   }
   if (impl == C2D_IMPL_AUTO && tc_ok) return attention_tc(p, B, s);
   return attention_simt(p, B, dtype, s);
+}
+
+int c2d_xattn_supported(int C, int heads, int Nq, int T, int T2, int dtype) {
+  return dtype == C2D_BF16 && xattn_tc_supported(C, heads, Nq, T, T2) ? 1 : 0;
+}
+
+long long c2d_xattn_packed_bytes(int C, int heads, int T, int T2) { return xattn_packed_bytes(C, heads, T, T2); }
+
+int c2d_xattn_pack_kv(const void* k, const void* v, long long ldkv, long long bskv, int T, const void* k2, const void* v2,
+                      long long ldkv2, long long bskv2, int T2, void* packed, int B, int C, int heads, int dtype, void* stream) {
+  C2D_REQUIRE(k && v && packed, "xattn_pack_kv: null pointer");
+  C2D_REQUIRE(B > 0 && C > 0 && heads > 0 && T > 0 && T2 >= 0 && ldkv >= C, "xattn_pack_kv: bad dims");
+  if (dtype != C2D_BF16) {
+    set_error("xattn_pack_kv: the fused cross-attention kernel is bf16 / tcgen05 only");
+    return C2D_ERR_UNSUPPORTED;
+  }
+  return xattn_pack_kv(k, v, ldkv, bskv, T, k2, v2, ldkv2, bskv2, T2, packed, B, C, heads, (cudaStream_t)stream);
+}
+
+int c2d_xattn_fwd(const void* x, long long ldx, const void* wq, const float* q_bias, const long long* ln_row_stats,
+                  const float* ln_colsum, float ln_eps, const void* kv_packed, int T, int T2, float lambda2, void* o,
+                  long long ldo, int B, int Nq, int C, int heads, float scale, int dtype, void* stream) {
+  C2D_REQUIRE(x && wq && kv_packed && o, "xattn_fwd: null pointer");
+  C2D_REQUIRE(B > 0 && Nq > 0 && C > 0 && heads > 0 && T > 0 && T2 >= 0, "xattn_fwd: bad dims");
+  C2D_REQUIRE(ldx >= C && ldo >= C, "xattn_fwd: bad row strides");
+  C2D_REQUIRE(!ln_row_stats || ln_colsum, "xattn_fwd: folded LayerNorm needs ln_colsum");
+  if (dtype != C2D_BF16) {
+    set_error("xattn_fwd: the fused kernel is bf16 / tcgen05 only; compose c2d_linear + c2d_attention in fp32 mode");
+    return C2D_ERR_UNSUPPORTED;
+  }
+  return xattn_tc(x, ldx, wq, q_bias, ln_row_stats, ln_colsum, ln_eps, kv_packed, T, T2, lambda2, o, ldo, B, Nq, C, heads, scale,
+                  (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -101,8 +101,9 @@ class AudioAttnProcessor(nn.Module):
 
     # ---- per-step part -------------------------------------------------------------------------
     supports_ln_fold = True
+    supports_packed_kv = True
 
-    def attend(self, attn, hidden_states: torch.Tensor, kv: torch.Tensor, residual: Optional[torch.Tensor] = None,
+    def attend(self, attn, hidden_states: torch.Tensor, kv, residual: Optional[torch.Tensor] = None,
                scale: float = 1.0, ln_stats: Optional[torch.Tensor] = None,
                row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
         """to_q -> softmax(q k^T d^-1/2) v -> to_out[0] (+ residual).  hidden_states [B,N,C].
@@ -110,6 +111,18 @@ class AudioAttnProcessor(nn.Module):
         folded into the to_q GEMM (attn.ln_q, prepared by SD15UNet); row_stats: statistics accumulator of the output."""
         dt = hidden_states.dtype
         c = self._cache
+        out_lin = _to_out_linear(attn)
+        if isinstance(kv, ops.XattnKV) and not ops.xattn_supported(hidden_states, attn.heads, kv.T, kv.T2):
+            kv = kv.kv                       # token counts outside the fused kernel (tiny latents): three-kernel path
+        if isinstance(kv, ops.XattnKV):
+            # packed K/V cache (SD15UNet.prepare_conditioning): to_q + attention core are ONE kernel, Q stays on chip
+            sc = float(getattr(attn, "scale", (kv.C // attn.heads) ** -0.5)) * scale
+            if ln_stats is not None:
+                o = ops.xattn(hidden_states, kv, ln=attn.ln_q, ln_stats=ln_stats, scale=sc)
+            else:
+                o = ops.xattn(hidden_states, kv, wq=c.get(_weight(attn.to_q), dt, ("wq", id(attn))), scale=sc)
+            bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
+            return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual, row_stats=row_stats)
         C = kv.shape[-1] // 2
         if ln_stats is not None:
             q = ops.linear(hidden_states, None, ln=attn.ln_q, ln_stats=ln_stats)
@@ -117,7 +130,6 @@ class AudioAttnProcessor(nn.Module):
             q = ops.linear(hidden_states, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
         d = C // attn.heads
         o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=float(getattr(attn, "scale", d ** -0.5)) * scale)
-        out_lin = _to_out_linear(attn)
         bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
         return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual, row_stats=row_stats)
 

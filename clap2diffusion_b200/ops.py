@@ -307,6 +307,97 @@ def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, 
     return out
 
 
+class XattnKV:
+    """Packed, step-invariant K / V cache of one cross-attention site (c2d_xattn_pack_kv): per (batch, head) the exact
+    shared-memory image the fused kernel fetches with one bulk copy.  T text(+audio) keys, T2 decoupled audio keys."""
+    __slots__ = ("packed", "B", "C", "heads", "T", "T2", "kv")
+
+    def __init__(self, packed, B, C, heads, T, T2, kv=None):
+        self.packed, self.B, self.C, self.heads, self.T, self.T2 = packed, B, C, heads, T, T2
+        self.kv = kv          # the unpacked [B,T,2C] tensor, kept for token counts the fused kernel does not take
+
+    @property
+    def shape(self):          # identifies the cache layout (the sampler keys its captured graphs on it)
+        return ("xattn_kv", self.B, self.C, self.heads, self.T, self.T2)
+
+    def copy_(self, other: "XattnKV"):
+        """Refresh the buffers a CUDA graph was captured on with a new image batch's cache."""
+        assert self.shape == other.shape
+        if self.packed is not None:
+            self.packed.copy_(other.packed)
+        if self.kv is not None and other.kv is not None:
+            self.kv.copy_(other.kv)
+        return self
+
+
+def xattn_supported(x, heads: int, T: int, T2: int = 0) -> bool:
+    """True when the fused cross-attention kernel takes this site (bf16, SD-1.5 shapes); no device work."""
+    if TEST_DOUBLE:
+        return True
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 3:
+        return False
+    return bool(lib.c2d_xattn_supported(x.shape[-1], int(heads), x.shape[1], int(T), int(T2), _lib.BF16))
+
+
+def xattn_packable(C: int, heads: int, T: int, dtype, T2: int = 0) -> bool:
+    """True when c2d_xattn_pack_kv takes this site (bf16, head dims / key counts inside the fused kernel)."""
+    if dtype != torch.bfloat16:
+        return False
+    return True if TEST_DOUBLE else int(lib.c2d_xattn_packed_bytes(int(C), int(heads), int(T), int(T2))) > 0
+
+
+def xattn_pack_kv(kv, heads: int, kv2=None) -> XattnKV:
+    """kv [B,T,2C] = [K | V] of a site (text keys with the audio injected); kv2 [B,T2,2C]: decoupled second branch."""
+    _dev(kv)
+    B, T, C2 = kv.shape
+    C = C2 // 2
+    assert kv.stride(2) == 1 and kv.dtype == torch.bfloat16, "the fused cross-attention kernel is bf16 only"
+    T2 = 0
+    if kv2 is not None:
+        T2 = kv2.shape[1]
+        assert kv2.shape[0] == B and kv2.shape[2] == C2 and kv2.stride(2) == 1 and kv2.dtype == kv.dtype
+    nbytes = int(lib.c2d_xattn_packed_bytes(C, int(heads), T, T2))
+    if nbytes <= 0:
+        raise _lib.C2DError(f"xattn_pack_kv: shape outside the fused kernel (C={C} heads={heads} T={T} T2={T2})")
+    packed = torch.empty(B, nbytes // 2, device=kv.device, dtype=kv.dtype)
+    check(lib.c2d_xattn_pack_kv(kv.data_ptr(), kv[..., C:].data_ptr(), kv.stride(1), kv.stride(0), T,
+                                None if kv2 is None else kv2.data_ptr(), None if kv2 is None else kv2[..., C:].data_ptr(),
+                                0 if kv2 is None else kv2.stride(1), 0 if kv2 is None else kv2.stride(0), T2,
+                                packed.data_ptr(), B, C, int(heads), _dt(kv), _stream()), "xattn_pack_kv")
+    return XattnKV(packed, B, C, int(heads), T, T2, kv)
+
+
+def xattn(x, kvp: XattnKV, *, wq=None, q_bias=None, ln=None, ln_stats=None, scale: Optional[float] = None,
+          lambda2: float = 1.0, out=None):
+    """Fused cross-attention site, per-step part (c2d_xattn_fwd): to_q (+ folded LayerNorm) + softmax(q k^T) v in one
+    kernel.  x [B,Nq,C]; kvp from xattn_pack_kv; ln / ln_stats: LNFold of the preceding LayerNorm and the int64
+    [B*Nq,2] row statistics of x (then wq / q_bias come from `ln`); lambda2 scales the decoupled second branch.
+    Returns o [B,Nq,C] (input of to_out)."""
+    _dev(x)
+    if ln is not None:
+        wq, q_bias = ln.w, ln.bias
+        assert ln_stats is not None and ln_stats.dtype == torch.int64 and ln_stats.numel() == x.shape[0] * x.shape[1] * 2
+    B, Nq, C = x.shape
+    assert kvp.B == B and kvp.C == C and kvp.packed.dtype == x.dtype
+    assert x.stride(2) == 1 and x.stride(0) == Nq * x.stride(1), "x must be a uniformly strided [B*Nq, C] row matrix"
+    assert wq.shape == (C, C) and wq.is_contiguous() and wq.dtype == x.dtype
+    d = C // kvp.heads
+    if scale is None:
+        scale = d ** -0.5
+    if out is None:
+        out = torch.empty(B, Nq, C, device=x.device, dtype=x.dtype)
+    assert out.stride(2) == 1 and out.stride(0) == Nq * out.stride(1)
+    flops = 2.0 * B * Nq * C * C + 4.0 * B * Nq * (kvp.T + kvp.T2) * C
+    with _Timed(flops, _nb(x, wq, kvp.packed, out)):
+        check(lib.c2d_xattn_fwd(x.data_ptr(), x.stride(1), wq.data_ptr(), _ptr(_f32(q_bias, "q_bias")),
+                                _ptr(ln_stats) if ln is not None else None,
+                                _ptr(_f32(ln.colsum, "colsum")) if ln is not None else None,
+                                ln.eps if ln is not None else 0.0, kvp.packed.data_ptr(), kvp.T, kvp.T2, float(lambda2),
+                                out.data_ptr(), out.stride(1), B, Nq, C, kvp.heads, float(scale), _dt(x), _stream()),
+              "xattn_fwd")
+    return out
+
+
 def audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode: int, *, out=None):
     """AudioAttnProcessor context step (add / concat); see c2d.h."""
     _dev(ehs)

@@ -86,10 +86,20 @@ class CrossAttnProcessor:
         return ops.linear(encoder_hidden_states, attn.wkv)
 
     supports_ln_fold = True
+    supports_packed_kv = True
 
     def attend(self, attn: AttentionSite, hidden_states, kv, residual=None, scale: float = 1.0, ln_stats=None,
                row_stats=None):
+        """kv: cached [B,T,2C] tensor, or an ops.XattnKV (packed cache): then to_q + attention are ONE kernel."""
         C = attn.to_q.out_features
+        if isinstance(kv, ops.XattnKV) and not ops.xattn_supported(hidden_states, attn.heads, kv.T, kv.T2):
+            kv = kv.kv                       # token counts outside the fused kernel (tiny latents): three-kernel path
+        if isinstance(kv, ops.XattnKV):
+            if ln_stats is not None:
+                o = ops.xattn(hidden_states, kv, ln=attn.ln_q, ln_stats=ln_stats, scale=attn.scale * scale)
+            else:
+                o = ops.xattn(hidden_states, kv, wq=attn.to_q.weight, scale=attn.scale * scale)
+            return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual=residual, row_stats=row_stats)
         if ln_stats is not None:
             q = ops.linear(hidden_states, None, ln=attn.ln_q, ln_stats=ln_stats)
         else:
@@ -152,6 +162,7 @@ class SD15UNet:
         self.fused_gn = dtype == torch.bfloat16       # producer-side GroupNorm statistics (tcgen05 epilogues)
         self.fold_ln = dtype == torch.bfloat16        # norm1/2/3 folded into the QKV / to_q / GEGLU GEMMs
         self.conv_in_tc = dtype == torch.bfloat16     # conv_in on the tensor cores over a channel-padded (4 -> 8) input
+        self.fused_xattn = dtype == torch.bfloat16    # attn2 sites: to_q + attention in one kernel over a packed K/V cache
         self._gn_channels = 0
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
@@ -337,6 +348,10 @@ class SD15UNet:
                 out[n] = p.prepare(s, ehs, kw.get("audio"))
             else:
                 out[n] = None                   # opaque processor: called with encoder_hidden_states each step
+            kvt = out[n]
+            if (self.fused_xattn and torch.is_tensor(kvt) and getattr(p, "supports_packed_kv", False)
+                    and ops.xattn_packable(s.to_q.out_features, s.heads, kvt.shape[1], kvt.dtype)):
+                out[n] = ops.xattn_pack_kv(kvt, s.heads)     # per-(batch, head) smem images for the fused kernel
         return out
 
     # ------------------------------------------------------------------ forward

@@ -130,6 +130,31 @@ int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, i
                   long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl,
                   void* stream);
 
+/* ---- fused cross-attention site (bf16 / tcgen05 only).  Replaces, in ONE kernel per denoising step, the reference's
+ *  attn.to_q + head_to_batch_dim + get_attention_scores + bmm + batch_to_head_dim
+ *  (models/audio_attention_processor.py:114-131); Q is never written to memory:
+ *    q = LN?(x) Wq^T + q_bias      x [B*Nq][C] (row stride ldx), wq [C][C] (nn.Linear layout, heads*d rows);
+ *                                  ln_row_stats != NULL: x is the UN-normalised stream, wq = Wq diag(gamma),
+ *                                  ln_colsum / q_bias from c2d_pack_lnfold, ln_row_stats = int64 [B*Nq][2] fixed-point
+ *                                  (sum, sumsq) of the rows of x (see c2d_linear_ex)
+ *    o = softmax(q k^T scale) v  [ + lambda2 * softmax(q k2^T scale) v2 ]
+ *  k, v [B][T][heads*d] (T <= 96): the text keys / values with the audio injected ("add": T = 77, "concat": T = 81;
+ *  models/audio_attention_processor.py:85-121).  k2, v2 [B][T2][heads*d] (T2 <= 16, NULL / 0 = none): DECOUPLED audio
+ *  branch -- its own softmax, scaled by lambda2 and added (the gated second branch of models/audio_adapter_v4.py:208-261
+ *  when it shares the site's query).  o [B*Nq][heads*d] (row stride ldo) feeds to_out[0] (c2d_linear_ex).
+ *  K / V are step-invariant: c2d_xattn_pack_kv lays them out ONCE per image as per-(batch, head) shared-memory images
+ *  (c2d_xattn_packed_bytes(C, heads, T, T2) bytes per batch element, caller-owned) that the per-step kernel fetches
+ *  with one bulk copy per head.  Shapes outside the kernel return C2D_ERR_UNSUPPORTED (ask c2d_xattn_supported first;
+ *  c2d_xattn_packed_bytes returns 0 for them); nothing is silently routed elsewhere. */
+int c2d_xattn_supported(int C, int heads, int Nq, int T, int T2, int dtype);
+long long c2d_xattn_packed_bytes(int C, int heads, int T, int T2);
+int c2d_xattn_pack_kv(const void* k, const void* v, long long ldkv, long long bskv, int T, const void* k2, const void* v2,
+                      long long ldkv2, long long bskv2, int T2, void* packed, int B, int C, int heads, int dtype,
+                      void* stream);
+int c2d_xattn_fwd(const void* x, long long ldx, const void* wq, const float* q_bias, const long long* ln_row_stats,
+                  const float* ln_colsum, float ln_eps, const void* kv_packed, int T, int T2, float lambda2, void* o,
+                  long long ldo, int B, int Nq, int C, int heads, float scale, int dtype, void* stream);
+
 /* ---- AudioAttnProcessor context step (models/audio_attention_processor.py:85-109), step-invariant:
  *  ehs_out = ehs + sigmoid(alpha) * mean_K(W2.gelu(W1.a + b1) + b2)            (ADD,   Tout = T)
  *  ehs_out = [ehs ; adaptive_avg_pool_{<=4}(W2.gelu(W1.a + b1) + b2)]           (CONCAT, Tout = T+min(K,4))

@@ -417,3 +417,70 @@ def test_layernorm_folded_into_geglu():
     assert rel(y, ref) < 1e-2
     ref32 = T.geglu(T.linear(T.layer_norm(h, gamma, beta).float(), w, b))
     assert rel(y, ref32) < 1e-2
+
+
+# ------------------------------------------------------------------ fused cross-attention site
+XATTN = [
+    # B, Nq, C, T, T2, fold
+    (2, 4096, 320, 77, 0, True), (2, 1024, 640, 77, 0, True), (2, 256, 1280, 77, 0, True), (3, 64, 1280, 77, 0, True),
+    (2, 1024, 320, 81, 0, True), (2, 256, 640, 81, 0, False), (1, 128, 320, 77, 0, False),
+    (2, 512, 320, 77, 10, True), (2, 256, 640, 77, 16, True), (1, 256, 1280, 81, 10, True), (2, 128, 320, 20, 4, False),
+]
+
+
+@pytest.mark.parametrize("B,Nq,C,Tk,T2,fold", XATTN)
+def test_xattn_fused(B, Nq, C, Tk, T2, fold):
+    """c2d_xattn_fwd == to_q GEMM (folded LayerNorm) -> attention core, both as separate libc2d kernels and as torch fp32."""
+    heads, M = 8, B * Nq
+    assert ops.xattn_supported(torch.empty(B, Nq, C, device=DEV, dtype=BF16), heads, Tk, T2)
+    h = (rnd(M, C, dtype=BF16) * 1.5 + 0.2).view(B, Nq, C)
+    kv = rnd(B, Tk, 2 * C, dtype=BF16, seed=8)
+    kv2 = rnd(B, T2, 2 * C, dtype=BF16, seed=9) if T2 else None
+    w = rnd(C, C, scale=C ** -0.5, seed=6) * 2.0
+    lam = 0.37
+    kw = {}
+    if fold:
+        rs = torch.zeros(M * 2, device=DEV, dtype=torch.int64)
+        ident = torch.eye(C, device=DEV, dtype=BF16)
+        assert torch.equal(ops.linear(h, ident, row_stats=rs), h)              # statistics of h itself
+        gamma, beta = 1 + 0.2 * rnd(C, seed=4), 0.2 * rnd(C, seed=5)
+        ln = ops.pack_lnfold(w, gamma, beta, None, BF16)
+        kw = dict(ln=ln, ln_stats=rs)
+        q = ops.linear(h, None, ln=ln, ln_stats=rs)
+        q32 = T.linear(T.layer_norm(h, gamma, beta), w.to(BF16))
+    else:
+        qb = rnd(C, seed=7)
+        kw = dict(wq=w.to(BF16), q_bias=qb)
+        q = ops.linear(h, w.to(BF16), qb)
+        q32 = T.linear(h, w.to(BF16), qb)
+    o = ops.xattn(h, ops.xattn_pack_kv(kv, heads, kv2), lambda2=lam, **kw)
+    ref = ops.attention(q, kv[..., :C], kv[..., C:], heads).float()
+    ref32 = T.attention(q32, kv[..., :C], kv[..., C:], heads).float()
+    if T2:
+        ref = ref + lam * ops.attention(q, kv2[..., :C], kv2[..., C:], heads).float()
+        ref32 = ref32 + lam * T.attention(q32, kv2[..., :C], kv2[..., C:], heads).float()
+    assert torch.isfinite(o.float()).all()
+    assert rel(o, ref) < 1e-2, "vs the three-kernel libc2d composition"
+    assert rel(o, ref32) < 1e-2, "vs torch fp32"
+
+
+def test_xattn_strided_views_and_unsupported():
+    B, Nq, C, heads = 2, 256, 320, 8
+    big = rnd(B * Nq, 2 * C, dtype=BF16)
+    x = big[:, :C].view(B, Nq, C) if False else big.view(B, Nq, 2 * C)[..., :C]       # row stride 2C
+    kv = rnd(B, 77, 2 * C, dtype=BF16, seed=8)
+    w = rnd(C, C, dtype=BF16, scale=C ** -0.5, seed=6)
+    out = torch.zeros(B, Nq, 2 * C, device=DEV, dtype=BF16)
+    kvp = ops.xattn_pack_kv(torch.cat([kv, kv], -1)[..., 2 * C:], heads)                 # strided [K | V] view (row stride 4C)
+    ops.xattn(x, kvp, wq=w, out=out[..., C:])
+    ref = T.attention(T.linear(x, w), kv[..., :C], kv[..., C:], heads)
+    assert rel(out[..., C:], ref) < 1e-2 and float(out[..., :C].abs().max()) == 0.0
+    # shapes outside the kernel are refused loudly, never silently routed elsewhere
+    assert not ops.xattn_supported(torch.empty(1, 100, 320, device=DEV, dtype=BF16), 8, 77)
+    kv1 = ops.xattn_pack_kv(kv[:1], heads)
+    with pytest.raises(Exception):
+        ops.xattn(torch.zeros(1, 100, 320, device=DEV, dtype=BF16), kv1, wq=w)
+    with pytest.raises(Exception):
+        ops.xattn(torch.zeros(1, 128, 320, device=DEV, dtype=F32), kv1, wq=w.float())
+    with pytest.raises(Exception):
+        ops.xattn_pack_kv(torch.zeros(1, 200, 640, device=DEV, dtype=BF16), heads)

@@ -177,6 +177,50 @@ def attention(q, k, v, heads, *, scale=None, mask=None, out=None, impl=0):
     return o.to(q.dtype)
 
 
+def xattn_supported(x, heads, T, T2=0):
+    return True
+
+
+def xattn_packable(C, heads, T, dtype, T2=0):
+    return dtype == torch.bfloat16
+
+
+class _KV(real_ops.XattnKV):
+    def __init__(self, kv, kv2, heads):
+        super().__init__(None, kv.shape[0], kv.shape[2] // 2, heads, kv.shape[1], 0 if kv2 is None else kv2.shape[1], kv)
+        self.kv, self.kv2, self.heads = kv, kv2, heads
+        self.B, self.T, self.C = kv.shape[0], kv.shape[1], kv.shape[2] // 2
+        self.T2 = 0 if kv2 is None else kv2.shape[1]
+
+
+def xattn_pack_kv(kv, heads, kv2=None):
+    return _KV(kv, kv2, heads)
+
+
+def xattn(x, kvp, *, wq=None, q_bias=None, ln=None, ln_stats=None, scale=None, lambda2=1.0, out=None):
+    """q is rounded to the activation dtype (it is the bf16 A operand of the score MMA in the kernel)."""
+    C = x.shape[-1]
+    if ln is not None:
+        q = linear(x, None, ln=ln, ln_stats=ln_stats)
+    else:
+        q = linear(x, wq, q_bias)
+    o = _attn_probs_rounded(q, kvp.kv[..., :C], kvp.kv[..., C:], kvp.heads, scale)
+    if kvp.kv2 is not None:
+        o = o + lambda2 * _attn_probs_rounded(q, kvp.kv2[..., :C], kvp.kv2[..., C:], kvp.heads, scale)
+    return o.to(x.dtype)
+
+
+def _attn_probs_rounded(q, k, v, heads, scale):
+    B, Nq, C = q.shape
+    d = C // heads
+    scale = d ** -0.5 if scale is None else scale
+    qh = q.float().reshape(B, Nq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(B, -1, heads, d).transpose(1, 2)
+    vh = v.float().reshape(B, -1, heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, Nq, C)
+
+
 def audio_context(ehs, audio, w1, b1, w2, b2, alpha, mode, *, out=None):
     ap = F.linear(F.gelu(F.linear(audio.float(), w1.float(), b1)), w2.float(), b2)
     if mode == real_ops.AUDIO_ADD:
