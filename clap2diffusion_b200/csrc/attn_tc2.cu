@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const Attn2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_OFF_BAR);
   uint64_t* q_full = bars;                 // [1]
   uint64_t* k_full = bars + 1;             // [A2_ST]

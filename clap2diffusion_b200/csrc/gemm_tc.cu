@@ -191,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + TC_STAGES;
   uint64_t* tmem_full = empty + TC_STAGES;
@@ -477,7 +477,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
   using Cfg = Tc2Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;       // [2] accumulator ready
@@ -753,7 +753,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_n) {
   using Cfg = Tc3Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;

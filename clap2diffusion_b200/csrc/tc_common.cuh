@@ -11,6 +11,15 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte-aligned start of the dynamic shared memory (the 128B-swizzle atoms need it).  The offset is added to the
+// __shared__ array itself, NOT computed through a uintptr_t round trip: that would turn every later dereference into a
+// generic LD.E / ST.E, which takes the global-memory path before it is routed to shared memory (measured on B200:
+// ~17 cycles more per 16-byte access than LDS / STS; the GEMM epilogues stage whole tiles through shared memory).
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* smem_raw) {
+  const uint32_t a = smem_u32(smem_raw);
+  return smem_raw + ((1024u - (a & 1023u)) & 1023u);
+}
+
 // One lane of a CONVERGED warp.  tcgen05.mma / cp.async.bulk.tensor / tcgen05.commit are uniform-datapath
 // instructions: issued under this predicate from warp-uniform code, ptxas keeps their descriptors in uniform
 // registers; issued from an `if (lane == 0)` region it wraps every one of them in a lane-serialising loop with

@@ -143,7 +143,7 @@ template <int NBLK, int NCH>
 __global__ void __launch_bounds__(XA_THREADS, 2)
 xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const XaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.region_bytes);
   uint64_t* full = bars + 0;                 // [2]  phase-1 ring
   uint64_t* empty = bars + 2;                // [2]
