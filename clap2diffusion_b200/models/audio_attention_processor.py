@@ -6,6 +6,11 @@ Same class names, constructor arguments, ``state_dict()`` keys (``alpha``, ``aud
 ``proc(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
 **cross_attention_kwargs)`` with audio arriving as ``cross_attention_kwargs['audio'][level]``.
 
+Design extension (no reference counterpart, opt-in): ``mode="decoupled"`` -- the text keys stay untouched and the
+projected audio tokens get their own softmax through the site's to_k / to_v; the audio branch is scaled by
+sigmoid(alpha) and added before to_out (BASELINE.json north_star "fused decoupled text+audio cross-attention").
+It runs on the fused bf16 kernel only (``ops.xattn``); the reference treats the string as an unknown mode.
+
 What differs from the reference (by design, results identical):
   * the audio injection + K/V projections are step-invariant, so they are exposed separately
     (``prepare`` -> cached K/V, ``attend`` -> per-step work); ``__call__`` = prepare + attend;
@@ -93,9 +98,29 @@ class AudioAttnProcessor(nn.Module):
         self._cache._c[key] = (ver, w.contiguous())
         return self._cache._c[key][1]
 
+    def audio_features(self, audio_tokens: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+        """audio_proj(audio_tokens) [B,K,hidden] (reference :88, eval mode: no dropout)."""
+        a = audio_tokens if audio_tokens.dtype == dt else ops.cast(audio_tokens.contiguous(), dt)
+        l0, l3 = self.audio_proj[0], self.audio_proj[3]
+        c = self._cache
+        h = ops.linear(a.contiguous(), c.get(l0.weight, dt, "w1"), c.get(l0.bias, torch.float32, "b1"), act=ops.ACT_GELU)
+        return ops.linear(h, c.get(l3.weight, dt, "w2"), c.get(l3.bias, torch.float32, "b2"))
+
     def prepare(self, attn, encoder_hidden_states: torch.Tensor, audio: Optional[Dict[str, torch.Tensor]] = None):
-        """K/V for this site: [B, T', 2C] = context(ehs, audio[level]) @ [Wk; Wv]^T (reference :120-121)."""
+        """K/V for this site: [B, T', 2C] = context(ehs, audio[level]) @ [Wk; Wv]^T (reference :120-121).
+        mode="decoupled" (extension): a packed ops.XattnKV holding the text K/V and the audio branch's own K/V."""
         tokens = audio.get(self.level) if isinstance(audio, dict) else None
+        if self.mode == "decoupled" and tokens is not None:
+            dt = encoder_hidden_states.dtype
+            wkv = self._kv_weight(attn, dt)
+            C = wkv.shape[0] // 2
+            if tokens.shape[1] > 16 or not ops.xattn_packable(C, attn.heads, encoder_hidden_states.shape[1], dt, tokens.shape[1]):
+                raise C2DError("mode='decoupled' runs on the fused bf16 cross-attention kernel only "
+                               f"(<= 16 audio tokens, <= 96 text keys; got dtype {dt}, {tokens.shape[1]} audio tokens)")
+            kv = ops.linear(encoder_hidden_states.contiguous(), wkv)
+            kv2 = ops.linear(self.audio_features(tokens, dt), wkv)
+            lam = float(torch.sigmoid(self.alpha.detach().float()))     # once per image, outside the captured step
+            return ops.xattn_pack_kv(kv, attn.heads, kv2, lambda2=lam)
         ehs = self.context(encoder_hidden_states, tokens)
         return ops.linear(ehs, self._kv_weight(attn, ehs.dtype))
 
@@ -113,6 +138,9 @@ class AudioAttnProcessor(nn.Module):
         c = self._cache
         out_lin = _to_out_linear(attn)
         if isinstance(kv, ops.XattnKV) and not ops.xattn_supported(hidden_states, attn.heads, kv.T, kv.T2):
+            if kv.kv is None:
+                raise C2DError(f"mode='decoupled' needs the fused kernel; {hidden_states.shape[1]} tokens per sample is "
+                               "outside it (multiples of 128, or 32 / 64 / 96)")
             kv = kv.kv                       # token counts outside the fused kernel (tiny latents): three-kernel path
         if isinstance(kv, ops.XattnKV):
             # packed K/V cache (SD15UNet.prepare_conditioning): to_q + attention core are ONE kernel, Q stays on chip
@@ -167,6 +195,9 @@ class AudioAttnProcessor(nn.Module):
             if ehs.dtype != x.dtype:
                 ehs = ops.cast(ehs.contiguous(), x.dtype)
             kv = self.prepare(attn, ehs, cross_attention_kwargs.get("audio"))
+            if torch.is_tensor(kv) and ops.xattn_supported(x, attn.heads, kv.shape[1]) and ops.xattn_packable(
+                    x.shape[-1], attn.heads, kv.shape[1], x.dtype):
+                kv = ops.xattn_pack_kv(kv, attn.heads)       # bf16, SD-1.5 shapes: to_q + attention core in one kernel
             res = x if getattr(attn, "residual_connection", False) and nd != 4 else None
             out = self.attend(attn, x, kv, residual=res, scale=scale)
         if nd == 4:                                   # back to [B,C,H,W] (reference :137-138)

@@ -310,10 +310,11 @@ def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, 
 class XattnKV:
     """Packed, step-invariant K / V cache of one cross-attention site (c2d_xattn_pack_kv): per (batch, head) the exact
     shared-memory image the fused kernel fetches with one bulk copy.  T text(+audio) keys, T2 decoupled audio keys."""
-    __slots__ = ("packed", "B", "C", "heads", "T", "T2", "kv")
+    __slots__ = ("packed", "B", "C", "heads", "T", "T2", "kv", "lambda2")
 
-    def __init__(self, packed, B, C, heads, T, T2, kv=None):
+    def __init__(self, packed, B, C, heads, T, T2, kv=None, lambda2=1.0):
         self.packed, self.B, self.C, self.heads, self.T, self.T2 = packed, B, C, heads, T, T2
+        self.lambda2 = float(lambda2)      # scale of the decoupled second branch
         self.kv = kv          # the unpacked [B,T,2C] tensor, kept for token counts the fused kernel does not take
 
     @property
@@ -327,6 +328,7 @@ class XattnKV:
             self.packed.copy_(other.packed)
         if self.kv is not None and other.kv is not None:
             self.kv.copy_(other.kv)
+        self.lambda2 = other.lambda2
         return self
 
 
@@ -346,8 +348,9 @@ def xattn_packable(C: int, heads: int, T: int, dtype, T2: int = 0) -> bool:
     return True if TEST_DOUBLE else int(lib.c2d_xattn_packed_bytes(int(C), int(heads), int(T), int(T2))) > 0
 
 
-def xattn_pack_kv(kv, heads: int, kv2=None) -> XattnKV:
-    """kv [B,T,2C] = [K | V] of a site (text keys with the audio injected); kv2 [B,T2,2C]: decoupled second branch."""
+def xattn_pack_kv(kv, heads: int, kv2=None, lambda2: float = 1.0) -> XattnKV:
+    """kv [B,T,2C] = [K | V] of a site (text keys with the audio injected); kv2 [B,T2,2C]: decoupled second branch,
+    scaled by lambda2 when it is added."""
     _dev(kv)
     B, T, C2 = kv.shape
     C = C2 // 2
@@ -364,14 +367,15 @@ def xattn_pack_kv(kv, heads: int, kv2=None) -> XattnKV:
                                 None if kv2 is None else kv2.data_ptr(), None if kv2 is None else kv2[..., C:].data_ptr(),
                                 0 if kv2 is None else kv2.stride(1), 0 if kv2 is None else kv2.stride(0), T2,
                                 packed.data_ptr(), B, C, int(heads), _dt(kv), _stream()), "xattn_pack_kv")
-    return XattnKV(packed, B, C, int(heads), T, T2, kv)
+    return XattnKV(packed, B, C, int(heads), T, T2, kv if kv2 is None else None, lambda2)
 
 
 def xattn(x, kvp: XattnKV, *, wq=None, q_bias=None, ln=None, ln_stats=None, scale: Optional[float] = None,
-          lambda2: float = 1.0, out=None):
+          lambda2: Optional[float] = None, out=None):
     """Fused cross-attention site, per-step part (c2d_xattn_fwd): to_q (+ folded LayerNorm) + softmax(q k^T) v in one
     kernel.  x [B,Nq,C]; kvp from xattn_pack_kv; ln / ln_stats: LNFold of the preceding LayerNorm and the int64
-    [B*Nq,2] row statistics of x (then wq / q_bias come from `ln`); lambda2 scales the decoupled second branch.
+    [B*Nq,2] row statistics of x (then wq / q_bias come from `ln`); lambda2 scales the decoupled second branch
+    (default: the value the cache was packed with).
     Returns o [B,Nq,C] (input of to_out)."""
     _dev(x)
     if ln is not None:
@@ -384,6 +388,8 @@ def xattn(x, kvp: XattnKV, *, wq=None, q_bias=None, ln=None, ln_stats=None, scal
     d = C // kvp.heads
     if scale is None:
         scale = d ** -0.5
+    if lambda2 is None:
+        lambda2 = kvp.lambda2
     if out is None:
         out = torch.empty(B, Nq, C, device=x.device, dtype=x.dtype)
     assert out.stride(2) == 1 and out.stride(0) == Nq * out.stride(1)

@@ -338,7 +338,7 @@ class SD15UNet:
             if not n.endswith("attn2"):
                 continue
             p = s.processor
-            if isinstance(p, AudioAttnProcessor):
+            if isinstance(p, AudioAttnProcessor) and p.mode != "decoupled":
                 key = id(p)                     # one shared processor per level -> one context per level
                 if key not in ctx_cache:
                     audio = kw.get("audio")

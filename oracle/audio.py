@@ -283,6 +283,20 @@ def processor_call(psd, attn: Dict[str, T], heads: int, h: T, ehs: Optional[T],
     return F.linear(o, attn["to_out.0.weight"], attn["to_out.0.bias"])                # :134
 
 
+def processor_call_decoupled(psd, attn: Dict[str, T], heads: int, h: T, ehs: T, audio_tokens: T) -> T:
+    """DESIGN EXTENSION -- no counterpart in the reference (parity unpinned; pinned only by this definition).
+    mode="decoupled" of the product's AudioAttnProcessor (BASELINE.json north_star: "fused decoupled text+audio
+    cross-attention ... audio-branch scale and add"): the text keys stay untouched, the projected audio tokens
+    (the reference's audio_proj, :88) get their OWN softmax through the site's to_k / to_v, and the audio branch is
+    scaled by the reference's gate sigmoid(alpha) (:92) and added before to_out:
+        o = softmax(q K_t^T s) V_t + sigmoid(alpha) * softmax(q K_a^T s) V_a."""
+    ap = _lin(psd, "audio_proj.3", F.gelu(_lin(psd, "audio_proj.0", audio_tokens)))
+    q = F.linear(h, attn["to_q.weight"])
+    o = _heads_attention(q, F.linear(ehs, attn["to_k.weight"]), F.linear(ehs, attn["to_v.weight"]), heads)
+    o2 = _heads_attention(q, F.linear(ap, attn["to_k.weight"]), F.linear(ap, attn["to_v.weight"]), heads)
+    return F.linear(o + torch.sigmoid(psd["alpha"]) * o2, attn["to_out.0.weight"], attn["to_out.0.bias"])
+
+
 LEVEL_OF_SITE_RULES = (("mid_block", "mid"), ("down_blocks.0", "early"), ("down_blocks.1", "early"),
                        ("down_blocks.2", "late"), ("down_blocks.3", "late"), ("up_blocks.0", "late"),
                        ("up_blocks.1", "late"), ("up_blocks.2", "mid"), ("up_blocks.3", "mid"))

@@ -112,3 +112,33 @@ def test_gated_xattn(gold):
     with torch.no_grad():
         assert rel_l2(m(h, a), _t(g["out"])) < 1e-5
         assert rel_l2(m(h, a, _t(g["mask"]).to(DEV)), _t(g["out_masked"])) < 1e-5
+
+
+@pytest.mark.parametrize("N,C", [(4096, 320), (1024, 640), (256, 1280), (64, 1280)])
+def test_attn_processor_decoupled_mode(N, C):
+    """Design extension (no reference counterpart): separate text / audio softmaxes, audio branch scaled by
+    sigmoid(alpha) and added, all inside the fused kernel -- vs the oracle's definition in fp32."""
+    seed = 11
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    psd["alpha"] = torch.tensor([0.7])
+    ehs = _t(np_randn("ehs", (2, 77, 768)))
+    audio = _t(np_randn("audio10", (2, 10, 768))) * 0.3
+    asd = to_torch({k.split(".", 1)[1]: v for k, v in synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.").items()})
+    h = _t(np_randn(f"h_{N}_{C}", (2, N, C)))
+    ref = A.processor_call_decoupled(psd, asd, 8, h, ehs, audio)
+    ref_na = A.processor_call(psd, asd, 8, h, ehs, None)
+    site = _Site({k: v.to(DEV) for k, v in asd.items()})
+    proc = pproc.AudioAttnProcessor(level="mid", mode="decoupled")
+    proc.load_state_dict(psd)
+    proc = proc.to(DEV).eval()
+    n0 = ops._lib.launch_count()
+    with torch.no_grad():
+        out = proc(site, h.to(DEV).to(torch.bfloat16), encoder_hidden_states=ehs.to(DEV), audio={"mid": audio.to(DEV)})
+        assert (ops.lib.c2d_last_kernel() or b"").decode() != ""
+        out_na = proc(site, h.to(DEV).to(torch.bfloat16), encoder_hidden_states=ehs.to(DEV))
+    assert ops._lib.launch_count() > n0
+    assert rel_l2(out.float().cpu(), ref) < 2e-2
+    assert rel_l2(out_na.float().cpu(), ref_na) < 2e-2
+    assert rel_l2(ref, ref_na) > 5e-2           # the audio branch matters at this gate value
+    with pytest.raises(Exception):              # fp32 parity mode has no decoupled kernel: refused, not re-routed
+        proc(site, h.to(DEV), encoder_hidden_states=ehs.to(DEV), audio={"mid": audio.to(DEV)})

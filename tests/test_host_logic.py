@@ -153,6 +153,28 @@ def test_attn_processor_module(gold):
             assert rel_l2(o4.reshape(2, C, 64).transpose(1, 2)[:, rows], _t(g[f"out_add_{N}_{C}"])) < 5e-6
 
 
+def test_attn_processor_decoupled_mode():
+    """Design extension (no reference counterpart): text and audio branches with separate softmaxes, audio branch
+    scaled by sigmoid(alpha) and added -- host logic vs the oracle's definition."""
+    seed = 11
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    psd["alpha"] = torch.tensor([0.7])
+    ehs = _t(np_randn("ehs", (2, 77, 768)))
+    audio = _t(np_randn("audio10", (2, 10, 768))) * 0.3
+    C, N = 320, 128
+    asd = to_torch({k.split(".", 1)[1]: v for k, v in synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.").items()})
+    site = _Site(asd)
+    h = _t(np_randn(f"h_{N}_{C}", (2, N, C)))
+    proc = pproc.AudioAttnProcessor(level="mid", mode="decoupled").eval()
+    proc.load_state_dict(psd)
+    with torch_ops.installed(), torch.no_grad():
+        out = proc(site, h, encoder_hidden_states=ehs, audio={"mid": audio})
+        out_na = proc(site, h, encoder_hidden_states=ehs)                          # no audio: plain text cross-attention
+    assert rel_l2(out, A.processor_call_decoupled(psd, asd, 8, h, ehs, audio)) < 5e-6
+    assert rel_l2(out_na, A.processor_call(psd, asd, 8, h, ehs, None)) < 5e-6
+    assert rel_l2(out, out_na) > 1e-3
+
+
 def test_gated_xattn_module(gold):
     g = gold("gated_xattn.npz")
     m = padapter.AudioCrossAttention(320).eval()
@@ -187,7 +209,7 @@ def _build_unet(W, dtype=torch.float32, fused=False):
                 super().__init__(*a, **k)
 
             def __setattr__(self, k, v):
-                if k in ("fused_gn", "fold_ln", "fuse_geglu") and getattr(self, "_force", False):
+                if k in ("fused_gn", "fold_ln", "fuse_geglu", "fused_xattn") and getattr(self, "_force", False):
                     v = True
                 object.__setattr__(self, k, v)
         unet = _Fused(W["unet"], device="cpu", dtype=dtype)
@@ -237,8 +259,14 @@ def test_unet_fused_groupnorm_host_logic_vs_oracle(gold, W):
         from clap2diffusion_b200 import ops as _ops
         _ops.layer_norm = _no_norm          # torch_ops.installed() restores both on exit
         _ops.group_norm = _no_norm
+        fused_calls = []
+        _xattn = _ops.xattn
+        _ops.xattn = lambda *a, **k: (fused_calls.append(1), _xattn(*a, **k))[1]
+        kv = unet.prepare_conditioning(_t(PL.text_states("a beach"))[None], mgr.get_audio_kwargs(routed))
+        assert all(isinstance(v, _ops.XattnKV) for v in kv.values()) and len(kv) == 16      # packed K/V cache per attn2 site
         eps = unet(x, float(g["t"]), _t(PL.text_states("a beach"))[None],
                    cross_attention_kwargs=mgr.get_audio_kwargs(routed))
+    assert len(fused_calls) == 16           # every attn2 site went through the fused to_q + attention entry point
     assert rel_l2(eps, _t(g["eps"])) < 1e-4
 
 

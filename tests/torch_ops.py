@@ -182,28 +182,29 @@ def xattn_supported(x, heads, T, T2=0):
 
 
 def xattn_packable(C, heads, T, dtype, T2=0):
-    return dtype == torch.bfloat16
+    return True
 
 
 class _KV(real_ops.XattnKV):
-    def __init__(self, kv, kv2, heads):
-        super().__init__(None, kv.shape[0], kv.shape[2] // 2, heads, kv.shape[1], 0 if kv2 is None else kv2.shape[1], kv)
+    def __init__(self, kv, kv2, heads, lambda2=1.0):
+        super().__init__(None, kv.shape[0], kv.shape[2] // 2, heads, kv.shape[1], 0 if kv2 is None else kv2.shape[1], kv, lambda2)
         self.kv, self.kv2, self.heads = kv, kv2, heads
         self.B, self.T, self.C = kv.shape[0], kv.shape[1], kv.shape[2] // 2
         self.T2 = 0 if kv2 is None else kv2.shape[1]
 
 
-def xattn_pack_kv(kv, heads, kv2=None):
-    return _KV(kv, kv2, heads)
+def xattn_pack_kv(kv, heads, kv2=None, lambda2=1.0):
+    return _KV(kv, kv2, heads, lambda2)
 
 
-def xattn(x, kvp, *, wq=None, q_bias=None, ln=None, ln_stats=None, scale=None, lambda2=1.0, out=None):
+def xattn(x, kvp, *, wq=None, q_bias=None, ln=None, ln_stats=None, scale=None, lambda2=None, out=None):
     """q is rounded to the activation dtype (it is the bf16 A operand of the score MMA in the kernel)."""
     C = x.shape[-1]
     if ln is not None:
         q = linear(x, None, ln=ln, ln_stats=ln_stats)
     else:
         q = linear(x, wq, q_bias)
+    lambda2 = kvp.lambda2 if lambda2 is None else lambda2
     o = _attn_probs_rounded(q, kvp.kv[..., :C], kvp.kv[..., C:], kvp.heads, scale)
     if kvp.kv2 is not None:
         o = o + lambda2 * _attn_probs_rounded(q, kvp.kv2[..., :C], kvp.kv2[..., C:], kvp.heads, scale)
