@@ -4,19 +4,30 @@
 // (second key / value set with its own softmax, scaled by lambda and added).  Q never leaves the SM:
 //
 //   CTA = 128 rows of the residual stream x one group of G heads (G * dp <= 256 accumulator columns; dp = ceil16(d)).
-//   phase 1  Qacc[128, G*dp] = X[128, C] . Wq_g^T      tcgen05.mma SS, operands by TMA through a 2-stage ring; the weight box
-//            is 3-D {64 k, dp rows, G heads} over Wq[heads][d][C]: rows d..dp-1 of every head are out of bounds and arrive
-//            as zeros, so the head-padded layout the later MMAs need never exists in memory.
+//   phase 1  Qacc[128, G*dp] = X[128, C] . Wq_g^T      tcgen05.mma SS, operands by TMA through a 2-stage ring (the first two
+//            stages are issued before the TMEM allocation / CTA sync); the weight box is 3-D {64 k, dp rows, G heads} over
+//            Wq[heads][d][C]: rows d..dp-1 of every head are out of bounds and arrive as zeros, so the head-padded layout
+//            the later MMAs need never exists in memory.
 //   phase 2  thread = row: q = rstd (acc - mean colsum) + bias -> bf16, written back IN PLACE into TMEM (two per column),
 //            where it is the A operand of the score MMA (TS form).  No shared-memory round trip.
 //   phase 3  per head: S = Q_h K_h^T (TS, K-major K tile) -> single-pass softmax over <= 112 keys in registers (segment 1 =
 //            text keys, segment 2 = decoupled audio keys, each normalised on its own; segment 2 times lambda) -> bf16 P in
 //            place over S -> O_h = P V_h (TS, V MN-major straight from its natural layout) -> bf16 -> global.
-//            K / V tiles of the next heads stream into the (now idle) phase-1 ring memory.
+//            K / V of a head is ONE contiguous pre-swizzled image in the packed cache (xattn_pack_kv_kernel, once per
+//            image): a single cp.async.bulk per head into the (now idle) phase-1 ring memory.  Row-granular tensor boxes
+//            over the natural [B][T][2C] cache cost the TMA unit ~25 cycles per 80-byte row (measured: 3400-4300 cycles per
+//            head, the whole head pipeline waited on them).
+//            G >= 2: two score buffers, heads alternate -- the score MMA of head h+1 retires during the softmax of head h,
+//            and the softmax warps run softmax(h+1) before the epilogue of head h, so P V (h) is off their critical path.
+//            The output accumulator ALIASES the bf16 Q of heads 0 / 1 (dead once their score MMAs are issued; tcgen05.mma
+//            retires in issue order), which is what lets Q (G*dp/2) + 2 x 80 score columns fit 256 TMEM columns.
 //   warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = convert / softmax / epilogue.
-//   The phases of one CTA are serial; two CTAs per SM (<= 256 TMEM columns, <= 112 KB smem each) overlap one CTA's
-//   projection (tensor pipe) with the other's softmax (MUFU).  tcgen05.mma executes in issue order, so the score MMA of
-//   head h+1 is issued right behind P V of head h although it overwrites the P columns.
+//   Two CTAs per SM (<= 256 TMEM columns, <= 112 KB smem each) overlap one CTA's projection (tensor pipe) with the other's
+//   softmax (MUFU).
+//   Measured dead ends (B200): per-column masking / segment selects inside the softmax (if-converted: 3.5x the
+//   instructions); generic-pointer smem reads of the folded-LayerNorm vectors (LD.E instead of LDS: +550 cycles per 64
+//   columns, see align_smem_1024); half of the exponentials as an FMA-pipe polynomial (no gain: the warps wait on
+//   mbarriers, not on MUFU); four-chunk epilogue loads (register spills under the 168-register cap of 2 CTAs / SM).
 #include <float.h>
 #include <stdlib.h>
 
@@ -48,7 +59,7 @@ struct XaParams {
   float scale_log2, lambda2;
   int num_kb;                    // C / 64
   int region_bytes, stage_bytes, slots, slot_bytes, kvblk_bytes;
-  int tmem_cols, col_s, col_o;
+  int tmem_cols, col_s, col_s1, col_o;   // col_s1 != col_s: two score buffers, heads alternate (G >= 2)
   int heads;
   const uint8_t* kvp;            // packed K / V cache: [B][heads] images of slot_bytes (see xattn_pack_kv_kernel)
   long long* dbg;                // optional timeline of one mid-grid CTA: [role][64] clock64 stamps (C2D_XATTN_DBG)
@@ -151,11 +162,11 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* qbf_ready = bars + 5;            //      bf16 Q written back to TMEM (128 arrivals)
   uint64_t* kv_full = bars + 6;              // [3]
   uint64_t* kv_empty = bars + 9;             // [3]
-  uint64_t* s_full = bars + 12;
-  uint64_t* p_full = bars + 13;              //      128 arrivals
-  uint64_t* o_full = bars + 14;
-  uint64_t* o_free = bars + 15;              //      128 arrivals: O of the previous head is in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* s_full = bars + 12;              // [2]  one per score buffer
+  uint64_t* p_full = bars + 14;              // [2]  128 arrivals
+  uint64_t* o_full = bars + 16;
+  uint64_t* o_free = bars + 17;              //      128 arrivals: O of the previous head is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   float* s_cs = reinterpret_cast<float*>(smem + p.region_bytes + 256);     // [NG] column sums, head-padded
   float* s_qb = s_cs + 256;                                                // [NG] bias, head-padded
 
@@ -174,11 +185,17 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(q_done, 1);
     mbar_init(qbf_ready, 128);
     for (int i = 0; i < XA_MAX_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); }
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
     fence_barrier_init();
+    // the first ring stages go out before the TMEM allocation and the CTA-wide sync: their latency overlaps the setup
+    for (int kb = 0; kb < XA_STAGES && kb < p.num_kb; ++kb) {
+      uint8_t* st = smem + kb * p.stage_bytes;
+      mbar_arrive_expect_tx(&full[kb], (uint32_t)p.stage_bytes);
+      tma_load_2d(st, &tmX, &full[kb], kb * XA_BK, m0);
+      tma_load_3d(st + XA_A_BYTES, &tmW, &full[kb], kb * XA_BK, 0, head0);
+    }
   }
   if (warp == 1) tmem_alloc_n(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
@@ -189,7 +206,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     XA_STAMP();
-    for (int kb = 0; kb < p.num_kb; ++kb) {
+    for (int kb = XA_STAGES; kb < p.num_kb; ++kb) {
       const int s = kb % XA_STAGES;
       mbar_wait(&empty[s], ((uint32_t)(kb / XA_STAGES) & 1u) ^ 1u);
       XA_STAMP();
@@ -240,37 +257,47 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(qbf_ready, 0);
     XA_STAMP();
     tc_fence_after();
-    const uint32_t tmem_s = tmem_base + (uint32_t)p.col_s;
+    const bool dual = p.col_s1 != p.col_s;
+    const uint32_t tmem_s0 = tmem_base + (uint32_t)p.col_s, tmem_s1 = tmem_base + (uint32_t)p.col_s1;
     const uint32_t tmem_o = tmem_base + (uint32_t)p.col_o;
     const int ksteps_qk = p.dp >> 4, ksteps_pv = p.NS >> 4;
-    for (int hh = 0; hh < p.G; ++hh) {
-      const int sl = hh % p.slots;
+    // S_h = Q_h K_h^T into score buffer (h & 1) [dual] / the single buffer.  tcgen05.mma retires in issue order, so a
+    // score MMA may be issued right behind the P V MMA whose P columns (same buffer) it overwrites, and P V of head 0
+    // -- whose accumulator aliases the bf16 Q of heads 0 and 1 in dual mode -- right behind the score MMA of head 1.
+    auto issue_qk = [&](int hh) {
+      const int sl = hh % p.slots, bi = dual ? (hh & 1) : 0;
       mbar_wait(&kv_full[sl], (uint32_t)(hh / p.slots) & 1u);
       XA_STAMP();
       tc_fence_after();
-      const uint32_t kaddr = smem_u32(smem + sl * p.slot_bytes);
       if (elect_one()) {
-        // S = Q_h K_h^T.  Issued right behind P V of the previous head (whose P it overwrites): MMAs retire in order.
-        const uint64_t kd = make_desc_k_sw128(kaddr);
+        const uint64_t kd = make_desc_k_sw128(smem_u32(smem + sl * p.slot_bytes));
         const uint32_t tq = tmem_base + (uint32_t)(hh * (p.dp >> 1));
         for (int kk = 0; kk < ksteps_qk; ++kk)
-          umma_f16_ts(tmem_s, tq + (uint32_t)kk * 8, kd + (uint64_t)((kk >> 2) * (p.kvblk_bytes >> 4) + (kk & 3) * 2), idesc_qk,
+          umma_f16_ts(bi ? tmem_s1 : tmem_s0, tq + (uint32_t)kk * 8, kd + (uint64_t)((kk >> 2) * (p.kvblk_bytes >> 4) + (kk & 3) * 2), idesc_qk,
                       kk > 0 ? 1u : 0u);
-        umma_commit(s_full);
+        umma_commit(&s_full[bi]);
       }
       __syncwarp();
-      mbar_wait(p_full, (uint32_t)hh & 1u);
+    };
+    issue_qk(0);
+    if (dual && p.G > 1) issue_qk(1);
+    for (int hh = 0; hh < p.G; ++hh) {
+      const int sl = hh % p.slots, bi = dual ? (hh & 1) : 0;
+      const uint32_t use = dual ? (uint32_t)(hh >> 1) : (uint32_t)hh;      // how often this buffer has been used before
+      mbar_wait(&p_full[bi], use & 1u);
       if (hh > 0) mbar_wait(o_free, (uint32_t)(hh - 1) & 1u);
       XA_STAMP();
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t vd = make_desc_mn_sw128(kaddr + NBLK * p.kvblk_bytes, (uint32_t)p.kvblk_bytes, 1024);
+        const uint64_t vd = make_desc_mn_sw128(smem_u32(smem + sl * p.slot_bytes) + NBLK * p.kvblk_bytes, (uint32_t)p.kvblk_bytes, 1024);
         for (int kk = 0; kk < ksteps_pv; ++kk)            // 16 keys = 8 TMEM columns of P = 2 KB of V rows
-          umma_f16_ts(tmem_o, tmem_s + (uint32_t)kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk > 0 ? 1u : 0u);
+          umma_f16_ts(tmem_o, (bi ? tmem_s1 : tmem_s0) + (uint32_t)kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, kk > 0 ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[sl]);
       }
       __syncwarp();
+      const int nxt = dual ? hh + 2 : hh + 1;
+      if (nxt < p.G) issue_qk(nxt);
     }
   } else {
     // ===================== convert / softmax / epilogue (warps 2..5; thread = row) =====================
@@ -341,13 +368,19 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
     // ---- phase 3.  Softmax in registers, 16-column chunks, no per-column decisions: the few columns between the last
     //      key and the chunk boundary are overwritten with -inf in TMEM first (exp2 gives exactly 0).
-    const uint32_t tmem_s = tmem_base + (uint32_t)p.col_s + lane_off;
+    const bool dual = p.col_s1 != p.col_s;
+    const uint32_t tmem_s0 = tmem_base + (uint32_t)p.col_s + lane_off, tmem_s1 = tmem_base + (uint32_t)p.col_s1 + lane_off;
     const uint32_t tmem_o = tmem_base + (uint32_t)p.col_o + lane_off;
     const bool has2 = p.n2 > 0;
     constexpr int NC1 = NCH - 1;                      // chunks that always belong to segment 1
     const float sc = p.scale_log2;
-    for (int hh = 0; hh < p.G; ++hh) {
-      mbar_wait(s_full, (uint32_t)hh & 1u);
+    // software pipeline: softmax(h) then the epilogue of head h-1, whose P V ran meanwhile
+    for (int step = 0; step <= p.G; ++step) {
+     if (step < p.G) {
+      const int hh = step, bi = dual ? (hh & 1) : 0;
+      const uint32_t use = dual ? (uint32_t)(hh >> 1) : (uint32_t)hh;
+      const uint32_t tmem_s = bi ? tmem_s1 : tmem_s0;
+      mbar_wait(&s_full[bi], use & 1u);
       XA_STAMP();
       tc_fence_after();
       if (p.n1 < p.s2 || (has2 && p.n2 < 16)) {
@@ -432,9 +465,12 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[bi]);
       XA_STAMP();
-      // ---- O_h -> bf16 -> global (the score MMA of the next head runs meanwhile)
+     }
+     if (step >= 1) {
+      // ---- O_h -> bf16 -> global
+      const int hh = step - 1;
       mbar_wait(o_full, (uint32_t)hh & 1u);
       XA_STAMP();
       tc_fence_after();
@@ -461,6 +497,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         }
       }
+     }
     }
   }
   tc_fence_before();
@@ -474,7 +511,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 static inline bool xa_al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 struct XaPlan {
-  int G, dp, NG, nblk, s2, NS, slots, slot_bytes, kvblk_bytes, stage_bytes, region_bytes, tmem_cols, col_s, col_o, smem_bytes;
+  int G, dp, NG, nblk, s2, NS, slots, slot_bytes, kvblk_bytes, stage_bytes, region_bytes, tmem_cols, col_s, col_s1, col_o, smem_bytes;
 };
 
 // Picks the head grouping and the shared / tensor memory plan; false when the shape is outside the kernel's envelope.
@@ -501,9 +538,20 @@ static bool xa_plan(int C, int heads, int T, int T2, XaPlan& pl) {
   pl.slots = pl.G < XA_MAX_SLOTS ? pl.G : XA_MAX_SLOTS;
   while (pl.slots > 1 && pl.slots * pl.slot_bytes > (ring > budget ? ring : budget)) --pl.slots;
   pl.region_bytes = pl.slots * pl.slot_bytes > ring ? pl.slots * pl.slot_bytes : ring;
+  // TMEM: bf16 Q at [0, NG/2).  G >= 2 heads: two score buffers (heads alternate; the score MMA of the next head runs
+  // during this head's softmax) and the output accumulator ALIASES the bf16 Q of heads 0 and 1, which are dead once
+  // their score MMAs have been issued.  G == 1: one score buffer, separate accumulator.
   pl.col_s = pl.NG >> 1;
-  pl.col_o = pl.col_s + pl.NS;
-  const int cols = pl.col_o + pl.dp;
+  int cols;
+  if (pl.G >= 2 && pl.slots >= 2) {
+    pl.col_s1 = pl.col_s + pl.NS;
+    pl.col_o = 0;
+    cols = pl.col_s1 + pl.NS;
+  } else {
+    pl.col_s1 = pl.col_s;
+    pl.col_o = pl.col_s + pl.NS;
+    cols = pl.col_o + pl.dp;
+  }
   if (cols > 512) return false;
   pl.tmem_cols = cols <= 256 ? 256 : 512;
   pl.smem_bytes = pl.region_bytes + 256 + 2 * 256 * 4 + 1024;
@@ -626,7 +674,7 @@ int xattn_tc(const void* x, long long ldx, const void* wq, const float* qbias, c
   p.num_kb = C / XA_BK;
   p.region_bytes = pl.region_bytes; p.stage_bytes = pl.stage_bytes; p.slots = pl.slots; p.slot_bytes = pl.slot_bytes;
   p.kvblk_bytes = pl.kvblk_bytes;
-  p.tmem_cols = pl.tmem_cols; p.col_s = pl.col_s; p.col_o = pl.col_o;
+  p.tmem_cols = pl.tmem_cols; p.col_s = pl.col_s; p.col_s1 = pl.col_s1; p.col_o = pl.col_o;
   p.heads = heads;
   p.kvp = reinterpret_cast<const uint8_t*>(kv_packed);
   p.dbg = nullptr;
