@@ -52,6 +52,10 @@ struct TcParams {
   float ln_invK, ln_eps;
   // producer side of the same scheme: per-row fixed-point (sum, sumsq) of y accumulated over the N tiles
   unsigned long long* rowstats_out;
+  // split-K (CTA-pair kernel, small-M convolutions): CTA (x, z) reduces k-blocks [z * kb_per_split, ...) and writes its
+  // raw fp32 accumulator tile to partial[z][M][N]; splitk_finish_kernel sums the slices and applies the epilogue
+  float* partial;
+  int kb_per_split;
 };
 
 // raw fixed-point (sum, sumsq) of row m (zero when there is no folded LayerNorm / the row is out of range); split from
@@ -764,6 +768,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int m0 = ((pair / num_n) * 2 + (int)rank) * TC_BM, n0 = (pair % num_n) * BN;
+  // split-K: this cluster's slice of the reduction (the whole K without a partial buffer)
+  const int kb_begin = p.partial ? (int)blockIdx.y * p.kb_per_split : 0;
+  const int nkb = p.partial ? min(p.kb_per_split, p.num_k_blocks - kb_begin) : p.num_k_blocks;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -788,9 +795,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       x0 = rem - y0 * p.W;
     }
     const int nb = n0 + (int)rank * (BN / 2);          // this CTA's half of the B rows
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+    for (int it = 0; it < nkb; ++it) {
+      const int kb = kb_begin + it;
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
       if (elect_one()) {
         uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
@@ -816,7 +824,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * TC_BM, BN, 0, 0);
       const uint64_t desc0 = make_desc_k_sw128(smem_u32(smem));
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full[s], ph);
@@ -828,7 +836,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_f16_2sm(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(&empty[s]);                                   // frees the slot in both CTAs
-          if (kb == p.num_k_blocks - 1) umma_commit_2sm(tmem_full);     // both accumulators complete
+          if (kb == nkb - 1) umma_commit_2sm(tmem_full);                // both accumulators complete
         }
         __syncwarp();
       }
@@ -859,6 +867,35 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int NCHUNK = GEGLU ? BN / 64 : BN / 32;
+    if (!GEGLU && p.partial) {
+      // split-K slice: the raw fp32 accumulator goes to partial[z][m][n] through the same per-warp staging (coalesced
+      // 32-byte pieces of 8 rows per store instruction); bias / residual / statistics belong to splitk_finish_kernel
+      float* part = p.partial + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N;
+#pragma unroll 1
+      for (int c = half; c < NCHUNK; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        const int rsub = lane >> 2, g = lane & 3;
+        const int n = n0 + c * 32 + g * 8;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = u * 8 + rsub, m = m0 + q * 32 + rr;
+          if (m < p.M && n + 8 <= p.N) {              // split-K is only selected for N % 8 == 0
+            const float* sp = stage + (size_t)rr * Cfg::EPI_PITCH + g * 8;
+            float* dst = part + (size_t)m * p.N + n;
+            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(sp);
+            *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<const float4*>(sp + 4);
+          }
+        }
+        __syncwarp();
+      }
+    } else
 #pragma unroll 1
     for (int c = half; c < NCHUNK; c += 2) {
       // ---- TMEM -> registers -> (+bias, activation | GEGLU gate) -> per-warp fp32 staging [32 rows][32 cols]
@@ -973,8 +1010,78 @@ static int launch_tc3(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   }
   const int num_n = ceil_div(p.N, BN);
   const int pairs = num_n * ceil_div(ceil_div(p.M, TC_BM), 2);
-  gemm_tc3_kernel<BN, STAGES, CONV, GEGLU><<<2 * pairs, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_n);
+  const int splits = p.partial ? ceil_div(p.num_k_blocks, p.kb_per_split) : 1;
+  gemm_tc3_kernel<BN, STAGES, CONV, GEGLU><<<dim3(2 * pairs, splits), TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
+}
+
+// ---- split-K: y = sum_z partial[z] + bias + rowvec[m / rows_per_vec] + residual -> bf16, plus the per-channel
+// fixed-point statistics the fused epilogue would have produced (integer atomics: order independent).
+// Block = 8 rows x (N / 8) column groups; thread = 8 consecutive columns of one row.
+constexpr int SKF_ROWS = 4;
+__global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
+                                     const float* __restrict__ rowvec, int rows_per_vec, const bf16* __restrict__ residual,
+                                     long long ldr, bf16* __restrict__ y, long long ldy, int M, int N,
+                                     unsigned long long* __restrict__ stats, int stats_rows) {
+  const int ng = N >> 3;
+  const int g = threadIdx.x % ng, rsub = threadIdx.x / ng;
+  const int m = blockIdx.x * SKF_ROWS + rsub, n = g * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const bool ok = rsub < SKF_ROWS && m < M;
+  if (ok) {
+    for (int z = 0; z < splits; ++z) {
+      const float* src = partial + ((size_t)z * M + m) * N + n;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + n + j);
+    }
+    if (rowvec) {
+      const float* rv = rowvec + (size_t)(m / rows_per_vec) * N + n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(rv + j);
+    }
+    if (residual) {
+      float rr[8];
+      Vec8<bf16>::load(residual + (size_t)m * ldr + n, rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rr[j];
+    }
+    Vec8<bf16>::store(y + (size_t)m * ldy + n, v);
+  }
+  if (stats) {
+    // column sums over the block's rows through shared memory (one pass per moment), then one atomic per column
+    __shared__ float sh[SKF_ROWS][1280 + 8];
+    const int bimg = (blockIdx.x * SKF_ROWS) / stats_rows;          // stats_rows % SKF_ROWS == 0: one image per block
+#pragma unroll 1
+    for (int kind = 0; kind < 2; ++kind) {
+      if (rsub < SKF_ROWS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[rsub][n + j] = ok ? (kind ? v[j] * v[j] : v[j]) : 0.f;
+      }
+      __syncthreads();
+      for (int col = threadIdx.x; col < N; col += blockDim.x) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < SKF_ROWS; ++r) acc += sh[r][col];
+        atomicAdd(stats + ((size_t)bimg * N + col) * 2 + kind, (unsigned long long)__float2ll_rn(acc * STATS_SCALE));
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// per-device split-K workspace (allocated once at c2d_init; see conv3x3_tc)
+static float* g_splitk_ws[16] = {};
+constexpr size_t SPLITK_WS_BYTES = (size_t)32 << 20;
+static float* splitk_workspace() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 16) ? g_splitk_ws[dev] : nullptr;
 }
 
 // Kernel selection.  Measured on B200 (tools/bench_shapes.py): the persistent kernel wins on the GEGLU projection
@@ -1114,6 +1221,16 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
 
 static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// C2D_SPLITK=0 keeps the small-M convolutions on the un-split kernel (A/B runs)
+static bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_SPLITK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int Cin, int Cout, int stride, int up) {
   if (up || (stride != 1 && stride != 2)) return false;
   if (stride == 2 && ((H & 1) || (W & 1))) return false;
@@ -1161,6 +1278,31 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   p.stats = reinterpret_cast<unsigned long long*>(stats);
   p.stats_rows = Ho * Wo;
   if (pairk) {
+    // Small planes (8x8 latents: M = B * 64): the tile grid does not fill the machine while K = 9 Cin is long ->
+    // split the reduction over blockIdx.y (fp32 slices in the per-device workspace + one finishing pass).
+    const int ctas = 2 * ceil_div(Cout, BN) * ceil_div(ceil_div(p.M, TC_BM), 2);
+    float* ws = splitk_workspace();
+    int splits = 1;
+    if (splitk_enabled() && ws && ctas * 2 <= num_sms() * 2 && Cout % 8 == 0 && Cout <= 1280 && p.num_k_blocks >= 32) {
+      splits = (2 * num_sms() + ctas - 1) / ctas;                   // aim at two CTAs per SM
+      if (splits > 8) splits = 8;
+      while (splits > 1 && (size_t)splits * p.M * Cout * sizeof(float) > SPLITK_WS_BYTES) --splits;
+      if (p.stats && p.stats_rows % SKF_ROWS) splits = 1;
+    }
+    if (splits > 1) {
+      TcParams q = p;
+      q.partial = ws;
+      q.kb_per_split = ceil_div(p.num_k_blocks, splits);
+      q.bias = nullptr; q.rowvec = nullptr; q.residual = nullptr; q.stats = nullptr;
+      int rc = BN == 256 ? launch_tc3<256, 3, true, false>(tmA, tmA, tmB, q, s)
+                         : (BN == 160 ? launch_tc3<160, 4, true, false>(tmA, tmA, tmB, q, s) : launch_tc3<128, 4, true, false>(tmA, tmA, tmB, q, s));
+      if (rc) return rc;
+      const int nsl = ceil_div(p.num_k_blocks, q.kb_per_split);
+      const int threads = SKF_ROWS * (Cout / 8);
+      splitk_finish_kernel<<<ceil_div(p.M, SKF_ROWS), threads, 0, s>>>(ws, nsl, bias, rowvec, p.rows_per_vec, p.residual, p.ldr, p.y,
+                                                                      p.ldy, p.M, Cout, p.stats, p.stats_rows);
+      return check_launch("conv3x3_tc");
+    }
     if (BN == 256) return launch_tc3<256, 3, true, false>(tmA, tmA, tmB, p, s);
     if (BN == 160) return launch_tc3<160, 4, true, false>(tmA, tmA, tmB, p, s);
     return launch_tc3<128, 4, true, false>(tmA, tmA, tmB, p, s);
@@ -1175,7 +1317,11 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
 }
 
 int init_tc(int device) {
-  (void)device;
+  if (device >= 0 && device < 16 && !g_splitk_ws[device]) {
+    void* ws = nullptr;
+    if (cudaMalloc(&ws, SPLITK_WS_BYTES) == cudaSuccess) g_splitk_ws[device] = reinterpret_cast<float*>(ws);
+    else cudaGetLastError();          // no workspace: the small-M convolutions simply stay un-split
+  }
   return get_encode();
 }
 

@@ -196,7 +196,9 @@ def test_linear_ex_stats_and_kconcat(B, HW, N, K, K1, res):
 
 @pytest.mark.parametrize("B,H,Cin,Cout,stride", [(2, 32, 320, 640, 1), (2, 16, 640, 320, 1), (4, 8, 1280, 1280, 1),
                                                  (2, 32, 320, 320, 2), (1, 64, 128, 96, 1), (2, 4, 1280, 1280, 1), (2, 2, 1280, 1280, 1), (2, 4, 640, 640, 2),
-                                                 (2, 64, 8, 320, 1), (1, 16, 24, 64, 1)])
+                                                 (2, 64, 8, 320, 1), (1, 16, 24, 64, 1),
+                                                 # benchmark-batch 8x8 planes: the split-K path of the CTA-pair kernel
+                                                 (16, 8, 1280, 1280, 1), (16, 8, 2560, 1280, 1), (16, 16, 1280, 1280, 2)])
 def test_conv3x3_ex_stats(B, H, Cin, Cout, stride):
     x = rnd(B, H, H, Cin, dtype=BF16)
     w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), BF16)
