@@ -343,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epi_affine32<LNF>(ra, s_bias + c * 32, s_cs + c * 32, ln_rstd, -ln_mr, v);
           epi_affine32<LNF>(rg, s_bias + 64 + c * 32, s_cs + 64 + c * 32, ln_rstd, -ln_mr, gg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gg[j]);
+          for (int j = 0; j < 32; j += 2) gelu_mul2(v[j], v[j + 1], gg[j], gg[j + 1]);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
@@ -641,7 +641,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           epi_affine32<LNF>(ra, sb + c * 32, scs + c * 32, ln_rstd, -ln_mr, v);
           epi_affine32<LNF>(rg, sb + 64 + c * 32, scs + 64 + c * 32, ln_rstd, -ln_mr, gg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gg[j]);
+          for (int j = 0; j < 32; j += 2) gelu_mul2(v[j], v[j + 1], gg[j], gg[j + 1]);
         }
         float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
 #pragma unroll
@@ -926,10 +926,12 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_32x32(t_row + grp * 128 + 64 + sub * 32, rg);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float a = __uint_as_float(ra[j]) + s_bias[grp * 128 + sub * 32 + j];
-          const float g = __uint_as_float(rg[j]) + s_bias[grp * 128 + 64 + sub * 32 + j];
-          v[j] = a * gelu_fast(g);
+        for (int j = 0; j < 32; j += 2) {
+          v[j] = __uint_as_float(ra[j]) + s_bias[grp * 128 + sub * 32 + j];
+          v[j + 1] = __uint_as_float(ra[j + 1]) + s_bias[grp * 128 + sub * 32 + j + 1];
+          const float g0 = __uint_as_float(rg[j]) + s_bias[grp * 128 + 64 + sub * 32 + j];
+          const float g1 = __uint_as_float(rg[j + 1]) + s_bias[grp * 128 + 64 + sub * 32 + j + 1];
+          gelu_mul2(v[j], v[j + 1], g0, g1);
         }
       }
       float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
