@@ -27,7 +27,9 @@
 //   Measured dead ends (B200): per-column masking / segment selects inside the softmax (if-converted: 3.5x the
 //   instructions); generic-pointer smem reads of the folded-LayerNorm vectors (LD.E instead of LDS: +550 cycles per 64
 //   columns, see align_smem_1024); half of the exponentials as an FMA-pipe polynomial (no gain: the warps wait on
-//   mbarriers, not on MUFU); four-chunk epilogue loads (register spills under the 168-register cap of 2 CTAs / SM).
+//   mbarriers, not on MUFU); four-chunk epilogue loads (register spills under the 168-register cap of 2 CTAs / SM);
+//   transposing the output rows through shared memory for row-major 16-byte stores (58.8 vs 53.4 us: the extra shared-
+//   memory pass and index arithmetic cost more than the 32-line store instructions they replace).
 #include <float.h>
 #include <stdlib.h>
 
@@ -148,6 +150,13 @@ __device__ __forceinline__ uint32_t xa_pack(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// columns >= nv of the 16-column chunk C get a score of -inf (exp2 gives exactly 0)
+template <int C, int N>
+__device__ __forceinline__ void xa_mask_chunk(uint32_t (&s)[N], int nv) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i >= nv) s[C * 16 + i] = 0xff800000u;
+}
 // NBLK = ceil(d / 64) 64-column blocks per K / V tile; NCH = NS / 16 score chunks (5: <= 80 keys, 6: <= 96 or 80 + audio,
 // 7: 96 + audio).  With a decoupled audio branch its 16 columns are always the LAST chunk.
 template <int NBLK, int NCH>
@@ -383,10 +392,12 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(&s_full[bi], use & 1u);
       XA_STAMP();
       tc_fence_after();
-      if (p.n1 < p.s2 || (has2 && p.n2 < 16)) {
+      // keys past the end of a segment: in the common case only the LAST chunk of a segment is ragged and is masked in
+      // registers below; shorter key sets (several ragged chunks) overwrite the columns in TMEM first
+      const int last1 = has2 ? NCH - 2 : NCH - 1;                 // last chunk of segment 1
+      const bool reg_mask = p.n1 > last1 * 16;
+      if (!reg_mask) {
         for (int c = p.n1; c < p.s2; ++c) xa_st1(tmem_s + (uint32_t)c, 0xff800000u);
-        if (has2)
-          for (int c = p.s2 + p.n2; c < p.s2 + 16; ++c) xa_st1(tmem_s + (uint32_t)c, 0xff800000u);
         tmem_st_wait();
       }
       uint32_t s[NCH * 16];
@@ -398,6 +409,12 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int i = 0; i < 16; ++i) s[c * 16 + i] = t[i];
       }
       tmem_ld_wait();
+      if (has2) {
+        if (reg_mask) xa_mask_chunk<(NCH >= 2 ? NCH - 2 : 0)>(s, p.n1 - (NCH - 2) * 16);
+        xa_mask_chunk<NCH - 1>(s, p.n2);
+      } else if (reg_mask) {
+        xa_mask_chunk<NCH - 1>(s, p.n1 - (NCH - 1) * 16);
+      }
       XA_STAMP();
       // segment-1 maximum over the first NC1 chunks (four FMNMX3 chains); the last chunk joins it or is segment 2
       float ma = __uint_as_float(s[0]), mb = __uint_as_float(s[1]), mc = __uint_as_float(s[2]), md = __uint_as_float(s[3]);
