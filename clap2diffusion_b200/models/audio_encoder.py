@@ -122,7 +122,7 @@ class CLAPAudioEncoder(nn.Module):
             waves = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
         feats = self.tower.encode(waves)
         # the reference re-normalises the (already unit-norm) features (:174); kept for exact drop-in semantics
-        return ops.l2_normalize(feats, eps=0.0) if feats.is_cuda else feats / feats.norm(p=2, dim=-1, keepdim=True)
+        return ops.l2_normalize(feats, eps=0.0)
 
     def forward(self, audio, sample_rate: int = None) -> torch.Tensor:
         return self.encode_audio(audio, sample_rate)
@@ -146,10 +146,7 @@ class CLAPTextEncoder(nn.Module):
 
 def compute_audio_text_similarity(audio_embeds: torch.Tensor, text_embeds: torch.Tensor, temperature: float = 0.07) -> torch.Tensor:
     """Cosine-similarity logits between unit-norm audio and text embeddings, scaled by 1 / temperature (reference :286-)."""
-    if audio_embeds.is_cuda:
-        a = ops.l2_normalize(audio_embeds.float().contiguous(), eps=0.0)
-        t = ops.l2_normalize(text_embeds.float().contiguous(), eps=0.0)
-        return ops.linear(a, (t / temperature).contiguous())
-    a = audio_embeds / audio_embeds.norm(p=2, dim=-1, keepdim=True)
-    t = text_embeds / text_embeds.norm(p=2, dim=-1, keepdim=True)
-    return a @ t.t() / temperature
+    # CUDA only, like every libc2d-backed entry point: a CPU tensor raises C2DError inside ops (no fallback)
+    a = ops.l2_normalize(audio_embeds.float().contiguous(), eps=0.0)
+    t = ops.l2_normalize(text_embeds.float().contiguous(), eps=0.0)
+    return ops.linear(a, (t / temperature).contiguous())
