@@ -75,6 +75,17 @@ __device__ __forceinline__ void ln_row_finish(const TcParams& p, const longlong2
     mr = mean * rstd;
   }
 }
+// (d0, d1) = (a0, a1) * (b, b) + (c0, c1) on the packed FFMA2 pipe
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
 // out[j] = acc[j] + bias[j]  |  folded LayerNorm: rstd * acc[j] - (mean * rstd) * colsum[j] + bias[j]; bias / colsum are
 // 16-byte aligned smem slices read as float4 (the epilogue of the short-K GEMMs is instruction-bound)
 template <bool LN>
@@ -84,11 +95,13 @@ __device__ __forceinline__ void epi_affine32(const uint32_t (&r)[32], const floa
   for (int j = 0; j < 32; j += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
     if (LN) {
+      // packed f32x2 FMAs: (colsum, colsum') * nmr + (bias, bias'), then (acc, acc') * rstd + that
       const float4 c4 = *reinterpret_cast<const float4*>(scs + j);
-      v[j] = fmaf(__uint_as_float(r[j]), rstd, fmaf(nmr, c4.x, b4.x));
-      v[j + 1] = fmaf(__uint_as_float(r[j + 1]), rstd, fmaf(nmr, c4.y, b4.y));
-      v[j + 2] = fmaf(__uint_as_float(r[j + 2]), rstd, fmaf(nmr, c4.z, b4.z));
-      v[j + 3] = fmaf(__uint_as_float(r[j + 3]), rstd, fmaf(nmr, c4.w, b4.w));
+      float t0, t1, t2, t3;
+      ffma2v(t0, t1, c4.x, c4.y, nmr, b4.x, b4.y);
+      ffma2v(t2, t3, c4.z, c4.w, nmr, b4.z, b4.w);
+      ffma2v(v[j], v[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), rstd, t0, t1);
+      ffma2v(v[j + 2], v[j + 3], __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), rstd, t2, t3);
     } else {
       v[j] = __uint_as_float(r[j]) + b4.x;
       v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
@@ -687,10 +700,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
           }
+          if (!GEGLU) {                 // the GEGLU projection never feeds a GroupNorm: no channel statistics
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+            for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+          }
         }
-        if (p.stats) {
+        if (!GEGLU && p.stats) {
           const int bimg = mrow0 / p.stats_rows;
           stats_commit(ssum, ssq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
         }

@@ -319,7 +319,8 @@ class XattnKV:
 
     @property
     def shape(self):          # identifies the cache layout (the sampler keys its captured graphs on it)
-        return ("xattn_kv", self.B, self.C, self.heads, self.T, self.T2)
+        # lambda2 is a kernel ARGUMENT (baked into a captured graph), so it is part of the identity
+        return ("xattn_kv", self.B, self.C, self.heads, self.T, self.T2, self.lambda2)
 
     def copy_(self, other: "XattnKV"):
         """Refresh the buffers a CUDA graph was captured on with a new image batch's cache."""
@@ -328,7 +329,6 @@ class XattnKV:
             self.packed.copy_(other.packed)
         if self.kv is not None and other.kv is not None:
             self.kv.copy_(other.kv)
-        self.lambda2 = other.lambda2
         return self
 
 
