@@ -13,9 +13,11 @@
 //   warps 2..5  softmax: thread = query row.  ONE pass over S in the common case: p = exp2(s*scale - m_ref)
 //               against a LAGGING reference max; the largest probability is tracked on the packed bf16 bits,
 //               and only when it exceeds 2^8 is the tile redone with a new reference and the O accumulator
-//               rescaled in TMEM.  P goes to a double-buffered swizzled smem tile (generic-proxy writes +
-//               proxy fence).  Final 1/l normalisation and 16-byte bf16 stores.
-// For d <= 64 (S 2x64 + O <= 64 TMEM columns, ~97 KB smem) two CTAs share an SM.
+//               rescaled in TMEM.  P (bf16) is written back IN PLACE over its S buffer in TMEM and is the A operand
+//               of the P V MMA (TS form): no shared-memory round trip, no proxy fence; the score MMA of tile t+2 is
+//               issued behind P V (t) (tcgen05.mma retires in issue order).  Final 1/l normalisation and 16-byte
+//               bf16 stores.
+// For d <= 128 (S 2x64 + O <= 128 TMEM columns, <= 97 KB smem) two CTAs share an SM.
 // Measured alternatives that were slower on B200 (kept out): S triple-buffering, row sums on the tensor core
 // (P x ones), 8 softmax warps with a per-key-half split -- the kernel is bounded by TMEM-read + MUFU.EX2
 // throughput (ncu: pipe_tc ~58 %, xu ~50 %), not by warp-level latency hiding.
@@ -47,15 +49,14 @@ struct AttnTcParams {
 
 template <int NBLK>
 struct AtCfg {
-  static constexpr int KS = NBLK == 3 ? 2 : 3;               // K ring depth
-  static constexpr int VS = NBLK == 3 ? 2 : 3;               // V ring depth
+  static constexpr int KS = NBLK >= 2 ? 2 : 3;               // K ring depth
+  static constexpr int VS = NBLK >= 2 ? 2 : 3;               // V ring depth
   static constexpr int Q_BYTES = NBLK * AT_QTILE;
   static constexpr int KV_BYTES = NBLK * AT_KTILE;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + VS * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * AT_QTILE;       // P: 2 x [128 rows x 64 keys] bf16
+  static constexpr int OFF_BAR = OFF_V + VS * KV_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 template <int NBLK>
-__global__ void __launch_bounds__(AT_THREADS, NBLK == 1 ? 2 : 1)
+__global__ void __launch_bounds__(AT_THREADS, NBLK <= 2 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using Cfg = AtCfg<NBLK>;
@@ -141,7 +142,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t idesc_pv = make_idesc_bf16(128, p.npv, 0, 1);          // B (= V) is MN-major
     const uint64_t q_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_Q));
     const uint64_t k_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_K));
-    const uint64_t p_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_P));
     const uint64_t v_desc = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_V), AT_KTILE, 1024);
     const int ksteps = (p.d + 15) >> 4;
     auto issue_qk = [&](int t) {
@@ -171,12 +171,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(&v_full[vs], (uint32_t)(j / VS) & 1u);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t pd = p_desc + (uint64_t)(pb * (AT_QTILE >> 4));
+        const uint32_t tmem_p = tmem_base + (uint32_t)pb * AT_BK;          // bf16 P, in place over S[pb]
         const uint64_t vd = v_desc + (uint64_t)(vs * (Cfg::KV_BYTES >> 4));
 #pragma unroll
         for (int kk = 0; kk < AT_BK / 16; ++kk) {
-          // V tile: [64 keys][64-col blocks]; 16 keys = 2 groups of 8 rows (SBO = 1024 B), col blocks 8 KB apart (LBO)
-          umma_f16(tmem_o, pd + (uint64_t)(kk * 2), vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          // 16 keys = 8 TMEM columns of P; V tile: [64 keys][64-col blocks]; 16 keys = 2 groups of 8 rows (SBO = 1024 B),
+          // col blocks 8 KB apart (LBO)
+          umma_f16_ts(tmem_o, tmem_p + (uint32_t)kk * 8, vd + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&p_empty[pb]);
         umma_commit(&v_empty[vs]);
@@ -191,13 +192,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const int rsw = row & 7;
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const int pb = j & 1;
       const int kvalid = min(AT_BK, p.Nkv - j * AT_BK);
       const uint32_t tmem_s = tmem_base + (uint32_t)pb * AT_BK + lane_off;
-      uint8_t* p_row = smem + Cfg::OFF_P + pb * AT_QTILE + row * 128;
       mbar_wait(&s_full[pb], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       if (j == 0) {
@@ -214,17 +213,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         m_ref = mx * p.scale_log2;
       }
-      if (j >= 2) mbar_wait(&p_empty[pb], (uint32_t)((j - 2) >> 1) & 1u);     // PV(j-2) retired: P[pb] is free
+      // S(j) -> registers once: P overwrites these columns in place, a redone tile works from the registers
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(tmem_s, ra);
+      tmem_ld_32x32(tmem_s + 32, rb);
+      tmem_ld_wait();
       float sum;
       float alpha = 1.f;
       bool redo = false;
       for (;;) {
         sum = 0.f;
         uint32_t pmax2 = 0u;           // running max of the packed bf16 probabilities (p >= 0: bit patterns are ordered)
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tmem_s, ra);
-        tmem_ld_32x32(tmem_s + 32, rb);
-        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t (&r)[32] = c ? rb : ra;
@@ -250,13 +249,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               pmax2 = __vmaxu2(pmax2, packed[i >> 1]);
             }
           }
-          // 32 keys = 4 chunks of 16 B; chunk index within the 128 B row = c * 4 + q, XOR-swizzled by the row
+          // 32 keys = 16 packed columns at [c * 16, c * 16 + 16) of this S buffer
+          uint32_t lo[8], hi[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c * 4 + q) ^ rsw;
-            *reinterpret_cast<uint4*>(p_row + (chunk << 4)) =
-                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-          }
+          for (int q = 0; q < 8; ++q) { lo[q] = packed[q]; hi[q] = packed[8 + q]; }
+          tmem_st_32x8(tmem_s + (uint32_t)c * 16, lo);
+          tmem_st_32x8(tmem_s + (uint32_t)c * 16 + 8, hi);
         }
         if (redo) break;
         // largest probability of the row, as bf16 bits: > 2^8 means the row max ran ahead of the reference
@@ -267,14 +265,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float mnew = m_ref + __log2f(__uint_as_float(pm << 16));
         if (__any_sync(0xffffffffu, need && pm >= 0x7F80u)) {
           float mx = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_s + c * 32, r);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (i < kvalid) mx = fmaxf(mx, __uint_as_float(ra[i]));
+            if (32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(rb[i]));
           }
           mnew = mx * p.scale_log2;
         }
@@ -305,8 +299,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_st_wait();
       }
       l_run = l_run * alpha + sum;
+      tmem_st_wait();                 // P (and a rescaled O) are in TMEM
       tc_fence_before();
-      fence_proxy_async();            // P writes (generic proxy) -> visible to tcgen05.mma (async proxy)
       mbar_arrive(&p_full[pb]);       // also tells the MMA warp that S[pb] has been consumed
     }
     // ---- epilogue: O / l -> bf16 -> global
