@@ -427,6 +427,10 @@ XATTN = [
     (2, 4096, 320, 77, 0, True), (2, 1024, 640, 77, 0, True), (2, 256, 1280, 77, 0, True), (3, 64, 1280, 77, 0, True),
     (2, 1024, 320, 81, 0, True), (2, 256, 640, 81, 0, False), (1, 128, 320, 77, 0, False),
     (2, 512, 320, 77, 10, True), (2, 256, 640, 77, 16, True), (1, 256, 1280, 81, 10, True), (2, 128, 320, 20, 4, False),
+    # edges: partial row tiles (32 / 96 tokens per sample), the 7-chunk instances (96 keys + 16 audio keys) at every
+    # head-dim class, very short key sets (TMEM-store masking path), single keys
+    (3, 96, 320, 77, 0, True), (1, 32, 640, 96, 16, True), (2, 128, 1280, 96, 16, False), (2, 128, 320, 96, 16, True),
+    (2, 256, 640, 5, 0, False), (1, 128, 320, 1, 1, False), (5, 64, 320, 81, 3, True),
 ]
 
 
