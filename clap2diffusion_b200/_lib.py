@@ -48,6 +48,7 @@ SIGNATURES = {
     "c2d_geglu_linear_ex": [_p, _p, _p, _p, _p, _f, _p, _i, _i, _i, _i, _p],
     "c2d_pack_lnfold": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "c2d_conv3x3_ex": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p],
+    "c2d_conv3x3_down": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "c2d_channel_stats": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_group_norm_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p],
     "c2d_layer_norm": [_p, _p, _p, _p, _i, _i, _f, _i, _p],

@@ -7,13 +7,13 @@ namespace c2d {
 int linear_simt(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int,
                 int, int, int, cudaStream_t);
 int conv3x3_simt(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int,
-                 int, int, cudaStream_t);
+                 int, int, cudaStream_t, int pad = 1);
 bool linear_tc_supported(const void*, const void*, int, int, int, int);
 int linear_tc(const void*, const void*, const float*, const float*, int, const void*, void*, int, int, int, int, int, int,
               int, bool, const GemmExtras*, cudaStream_t);
 bool conv3x3_tc_supported(const void*, const void*, int, int, int, int, int, int, int);
 int conv3x3_tc(const void*, const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int,
-               long long*, cudaStream_t);
+               long long*, cudaStream_t, int pad = 1);
 int attention_simt(const AttnParams&, int, int, cudaStream_t);
 int attention_small(const AttnParams&, int, int, cudaStream_t);
 bool attention_tc_supported(const AttnParams&, int B);
@@ -121,6 +121,27 @@ int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float*
   int rc = conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, fused ? chan_stats : nullptr, (cudaStream_t)stream);
   if (rc || !chan_stats || fused) return rc;
   return c2d_channel_stats(y, chan_stats, B, HWo, Cout, dtype, stream);
+}
+
+int c2d_conv3x3_down(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
+                     long long* chan_stats, int dtype, int impl, void* stream) {
+  C2D_REQUIRE(x && w && y, "conv3x3_down: null pointer");
+  C2D_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && H % 2 == 0 && W % 2 == 0, "conv3x3_down: bad dims (H, W must be even)");
+  C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "conv3x3_down: bad dtype %d", dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tc_ok = dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, 2, 0);
+  if (impl == C2D_IMPL_TCGEN05) C2D_REQUIRE(tc_ok, "conv3x3_down: tcgen05 path needs bf16, pow2 output H/W, Cin %% 8 == 0");
+  if (tc_ok && impl != C2D_IMPL_SIMT) {
+    const int HWo = (H / 2) * (W / 2);
+    const bool fused = chan_stats && HWo % 32 == 0;
+    int rc = conv3x3_tc(x, w, bias, nullptr, nullptr, y, B, H, W, Cin, Cout, 2, fused ? chan_stats : nullptr, s, 0);
+    if (rc || !chan_stats || fused) return rc;
+    return c2d_channel_stats(y, chan_stats, B, HWo, Cout, dtype, stream);
+  }
+  int rc = conv3x3_simt(x, w, bias, nullptr, nullptr, y, B, H, W, Cin, Cout, 2, 0, dtype, s, 0);
+  if (rc || !chan_stats) return rc;
+  C2D_REQUIRE(dtype == C2D_BF16, "conv3x3_down: channel statistics exist on the bf16 path only");
+  return c2d_channel_stats(y, chan_stats, B, (H / 2) * (W / 2), Cout, dtype, stream);
 }
 
 int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,

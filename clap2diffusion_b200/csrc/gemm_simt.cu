@@ -24,7 +24,7 @@ struct SimtGemmParams {
   int act;
   int vec_a, vec_b;   // 8-wide vector loads legal for A / B
   // im2col geometry
-  int H, W, Cin, Ho, Wo, stride, up;
+  int H, W, Cin, Ho, Wo, stride, up, pad;
 };
 
 template <typename T>
@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_a(const SimtGemmParams& p, int m, int k0, f
     if (p.vec_a) {   // Cin % 8 == 0: the 8-chunk lies inside one tap
       int tap = k0 / p.Cin, c = k0 - tap * p.Cin;
       int ky = tap / 3, kx = tap - ky * 3;
-      int iy = oy * p.stride + ky - 1, ix = ox * p.stride + kx - 1;
+      int iy = oy * p.stride + ky - p.pad, ix = ox * p.stride + kx - p.pad;
       int Hin = p.up ? 2 * p.H : p.H, Win = p.up ? 2 * p.W : p.W;
       if (iy < 0 || iy >= Hin || ix < 0 || ix >= Win) {
 #pragma unroll
@@ -72,7 +72,7 @@ __device__ __forceinline__ void load_a(const SimtGemmParams& p, int m, int k0, f
         if (k < p.K) {
           int tap = k / p.Cin, c = k - tap * p.Cin;
           int ky = tap / 3, kx = tap - ky * 3;
-          int iy = oy * p.stride + ky - 1, ix = ox * p.stride + kx - 1;
+          int iy = oy * p.stride + ky - p.pad, ix = ox * p.stride + kx - p.pad;
           int Hin = p.up ? 2 * p.H : p.H, Win = p.up ? 2 * p.W : p.W;
           if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
             if (p.up) { iy >>= 1; ix >>= 1; }
@@ -193,11 +193,12 @@ int linear_simt(const void* x, const void* w, const float* bias, const float* ro
 }
 
 int conv3x3_simt(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y,
-                 int B, int H, int W, int Cin, int Cout, int stride, int up, int dtype, cudaStream_t s) {
+                 int B, int H, int W, int Cin, int Cout, int stride, int up, int dtype, cudaStream_t s, int pad) {
   SimtGemmParams p = {};
   int Hin = up ? 2 * H : H, Win = up ? 2 * W : W;
   p.Ho = (Hin - 1) / stride + 1;   // pad 1, k 3: floor((Hin + 2 - 3)/stride) + 1
-  p.Wo = (Win - 1) / stride + 1;
+  p.Wo = (Win - 1) / stride + 1;   // pad 0 + (0,1,0,1) padding, stride 2, even H / W: the same H/2 x W/2
+  p.pad = pad;
   p.x = x; p.w = w; p.bias = bias; p.rowvec = rowvec; p.residual = residual; p.y = y;
   p.M = B * p.Ho * p.Wo; p.N = Cout; p.K = 9 * Cin;
   p.ldx = 0; p.ldy = Cout; p.ldr = Cout;

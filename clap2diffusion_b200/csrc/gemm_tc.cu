@@ -39,6 +39,7 @@ struct TcParams {
   int num_k_blocks;
   // conv geometry (HW, W: OUTPUT plane; cstride: convolution stride 1 | 2)
   int HW, W, Cin, cblocks, cstride;
+  int cpad;        // leading zero padding of the 3x3 window: 1 (symmetric pad 1) | 0 (diffusers Downsample2D: pad right / bottom only)
   // optional per-channel statistics of y for the consuming GroupNorm: stats[b][n][{sum, sumsq}] as 2^20 fixed-point
   // 64-bit integers (integer atomics: the result does not depend on the order CTAs retire in); b = row / stats_rows
   unsigned long long* stats;
@@ -254,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int c0 = (kb - tap * p.cblocks) * TC_BK;
           const int ky = tap / 3, kx = tap - ky * 3;
           // stride-2: the tensor map traverses the input with element strides {1,2,2,1}
-          tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
+          tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - p.cpad, y0 * p.cstride + ky - p.cpad, b0);
           tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
         } else {
           if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
@@ -540,7 +541,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int tap = kb / p.cblocks;
             const int c0 = (kb - tap * p.cblocks) * TC_BK;
             const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
+            tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - p.cpad, y0 * p.cstride + ky - p.cpad, b0);
             tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
           } else {
             if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
@@ -824,7 +825,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int tap = kb / p.cblocks;
           const int c0 = (kb - tap * p.cblocks) * TC_BK;
           const int ky = tap / 3, kx = tap - ky * 3;
-          tma_load_4d_2sm(sA, &tmA, lbar, c0, x0 * p.cstride + kx - 1, y0 * p.cstride + ky - 1, b0);
+          tma_load_4d_2sm(sA, &tmA, lbar, c0, x0 * p.cstride + kx - p.cpad, y0 * p.cstride + ky - p.cpad, b0);
           tma_load_2d_2sm(sB, &tmB, lbar, tap * p.Cin + c0, nb);
         } else {
           if (kb < p.kb_split) tma_load_2d_2sm(sA, &tmA, lbar, kb * TC_BK, m0);
@@ -1257,7 +1258,7 @@ bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int
 }
 
 int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
-               int H, int W, int Cin, int Cout, int stride, long long* stats, cudaStream_t s) {
+               int H, int W, int Cin, int Cout, int stride, long long* stats, cudaStream_t s, int pad) {
   C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
               "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
   const int Ho = H / stride, Wo = W / stride;
@@ -1288,7 +1289,7 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   p.M = B * Ho * Wo; p.N = Cout; p.K = 9 * Cin; p.ldy = Cout; p.ldr = Cout;
   p.rows_per_vec = Ho * Wo;
   p.act = C2D_ACT_NONE;
-  p.HW = Ho * Wo; p.W = Wo; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK); p.cstride = stride;
+  p.HW = Ho * Wo; p.W = Wo; p.Cin = Cin; p.cblocks = ceil_div(Cin, TC_BK); p.cstride = stride; p.cpad = pad;
   p.num_k_blocks = 9 * p.cblocks;
   p.kb_split = p.num_k_blocks;
   if (stats) C2D_REQUIRE((Ho * Wo) % 32 == 0, "conv3x3_tc: channel statistics need Ho*Wo %% 32 == 0 (%d)", Ho * Wo);

@@ -212,6 +212,23 @@ def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, ups
     return out
 
 
+def conv3x3_down(x, w_packed, bias=None, *, out=None, impl=IMPL_AUTO, stats=None):
+    """diffusers Downsample2D(padding=0): zero-pad right / bottom by one, 3x3 convolution with stride 2.
+    x [B,H,W,Cin] NHWC (H, W even) -> [B,H/2,W/2,Cout]."""
+    _dev(x)
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    assert x.is_contiguous() and w_packed.is_contiguous() and tuple(w_packed.shape[1:]) == (3, 3, Cin) and H % 2 == 0 and W % 2 == 0
+    if out is None:
+        out = torch.empty(B, H // 2, W // 2, Cout, device=x.device, dtype=x.dtype)
+    if stats is not None:
+        assert stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == B * Cout * 2
+    with _Timed(2.0 * B * (H // 2) * (W // 2) * Cout * 9 * Cin, _nb(x, w_packed, out)):
+        check(lib.c2d_conv3x3_down(x.data_ptr(), w_packed.data_ptr(), _ptr(_f32(bias, "bias")), out.data_ptr(), B, H, W, Cin, Cout,
+                                   _ptr(stats), _dt(x), impl, _stream()), "conv3x3_down")
+    return out
+
+
 _gn_ws = {}
 
 

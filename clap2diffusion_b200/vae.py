@@ -61,12 +61,7 @@ class VAEDecoder:
         c = VAE_BLOCK_OUT[-1]
         self._conv("decoder.conv_in")
         self._resnet("decoder.mid_block.resnets.0", c, c)
-        a = "decoder.mid_block.attentions.0"
-        self._norm(f"{a}.group_norm")
-        wq, wk, wv = (self._dev32(f"{a}.{n}.weight") for n in ("to_q", "to_k", "to_v"))
-        self.w[f"{a}.qkv.weight"] = self._cast(torch.cat([wq, wk, wv], 0))
-        self.w[f"{a}.qkv.bias"] = torch.cat([self._dev32(f"{a}.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0).contiguous()
-        self._lin(f"{a}.to_out.0")
+        self._pack_attention("decoder.mid_block.attentions.0")
         self._resnet("decoder.mid_block.resnets.1", c, c)
         prev = c
         for i, cout in enumerate(reversed(VAE_BLOCK_OUT)):
@@ -113,9 +108,15 @@ class VAEDecoder:
         so = self._stats(B, cout, hw)
         return ops.conv3x3(h, w[f"{p}.conv2.weight"], w[f"{p}.conv2.bias"], residual=sc, impl=self.impl, stats=so), so
 
-    def _mid_attention(self, x, xs):
+    def _pack_attention(self, a):
+        self._norm(f"{a}.group_norm")
+        wq, wk, wv = (self._dev32(f"{a}.{n}.weight") for n in ("to_q", "to_k", "to_v"))
+        self.w[f"{a}.qkv.weight"] = self._cast(torch.cat([wq, wk, wv], 0))
+        self.w[f"{a}.qkv.bias"] = torch.cat([self._dev32(f"{a}.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0).contiguous()
+        self._lin(f"{a}.to_out.0")
+
+    def _mid_attention(self, x, xs, a="decoder.mid_block.attentions.0"):
         w = self.w
-        a = "decoder.mid_block.attentions.0"
         B, H, W, C = x.shape
         N = H * W
         xf = x.view(B, N, C)
@@ -157,6 +158,109 @@ class VAEDecoder:
         h = self._gn(h, hs, "decoder.conv_norm_out")
         h = ops.conv3x3(h, w["decoder.conv_out.weight"], w["decoder.conv_out.bias"], impl=self.impl)
         return ops.nhwc_to_nchw(h)
+
+
+class VAEEncoder(VAEDecoder):
+    """AutoencoderKL encoder + quant_conv of SD-1.5 (latents (4, 64, 64) as stored by the reference's
+    data/audiocaps_latent_v4.py:185) on the same kernels as the decoder.  The three Downsample2D(padding=0) layers are
+    `c2d_conv3x3_down` (zero padding on the right / bottom only: TMA out-of-bounds fill at an un-shifted window)."""
+
+    def _pack(self):
+        self._conv_any("encoder.conv_in")
+        prev = VAE_BLOCK_OUT[0]
+        for i, cout in enumerate(VAE_BLOCK_OUT):
+            for j in range(2):
+                self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+            if i < 3:
+                self._conv(f"encoder.down_blocks.{i}.downsamplers.0.conv")
+            prev = cout
+        c = VAE_BLOCK_OUT[-1]
+        self._resnet("encoder.mid_block.resnets.0", c, c)
+        self._pack_attention("encoder.mid_block.attentions.0")
+        self._resnet("encoder.mid_block.resnets.1", c, c)
+        self._norm("encoder.conv_norm_out")
+        self._conv("encoder.conv_out")
+        self._lin("quant_conv")
+        # encode(): posterior mode with the 0.18215 latent scaling folded into the four mean rows of quant_conv
+        wq = self._dev32("quant_conv.weight").reshape(8, 8)[:4] * VAE_SCALING
+        self.w["quant_conv.mean_scaled.weight"] = self._cast(wq.contiguous())
+        self.w["quant_conv.mean_scaled.bias"] = (self._dev32("quant_conv.bias")[:4] * VAE_SCALING).contiguous()
+
+    def _conv_any(self, p):
+        self._conv(p)
+
+    @torch.no_grad()
+    def _trunk(self, img: torch.Tensor) -> torch.Tensor:
+        """img fp32 NCHW [B,3,H,W] -> encoder.conv_out activations, NHWC [B,H/8,W/8,8]."""
+        w = self.w
+        x = ops.nchw_to_nhwc(img.contiguous().float(), self.dtype)
+        B = x.shape[0]
+        h = ops.conv3x3(x, w["encoder.conv_in.weight"], w["encoder.conv_in.bias"], impl=self.impl)
+        hs = None            # 512^2 / 256^2 levels: stand-alone statistics pass inside _gn (see FUSED_GN_MAX_HW)
+        for i in range(4):
+            for j in range(2):
+                h, hs = self._res(f"encoder.down_blocks.{i}.resnets.{j}", h, hs)
+            if i < 3:
+                n = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                hs = self._stats(B, w[f"{n}.weight"].shape[0], (h.shape[1] // 2) * (h.shape[2] // 2))
+                h = ops.conv3x3_down(h, w[f"{n}.weight"], w[f"{n}.bias"], impl=self.impl, stats=hs)
+        h, hs = self._res("encoder.mid_block.resnets.0", h, hs)
+        h, hs = self._mid_attention(h, hs, "encoder.mid_block.attentions.0")
+        h, hs = self._res("encoder.mid_block.resnets.1", h, hs)
+        h = self._gn(h, hs, "encoder.conv_norm_out")
+        return ops.conv3x3(h, w["encoder.conv_out.weight"], w["encoder.conv_out.bias"], impl=self.impl)
+
+    @torch.no_grad()
+    def moments(self, img: torch.Tensor):
+        """(mean, logvar) of the posterior, fp32 NCHW [B,4,H/8,W/8] each (logvar clamped to [-30, 20] like diffusers'
+        DiagonalGaussianDistribution; the clamp of this small diagnostic tensor is the one torch elementwise call here)."""
+        h = self._trunk(img)
+        m = ops.nhwc_to_nchw(ops.linear(h, self.w["quant_conv.weight"], self.w["quant_conv.bias"], impl=self.impl))
+        return m[:, :4].contiguous(), m[:, 4:].clamp(-30.0, 20.0).contiguous()
+
+    @torch.no_grad()
+    def encode(self, img: torch.Tensor) -> torch.Tensor:
+        """Scaled latents (posterior mode x 0.18215), fp32 NCHW [B,4,H/8,W/8]: what VAEDecoder.decode takes."""
+        h = self._trunk(img)
+        z = ops.linear(h, self.w["quant_conv.mean_scaled.weight"], self.w["quant_conv.mean_scaled.bias"], impl=self.impl)
+        return ops.nhwc_to_nchw(z)
+
+
+def encoder_param_shapes() -> Dict[str, tuple]:
+    """diffusers state-dict names -> shapes of the AutoencoderKL encoder + quant_conv (34,163,664)."""
+    out: Dict[str, tuple] = {}
+
+    def conv(n, cin, cout, k):
+        out[f"{n}.weight"] = (cout, cin, k, k)
+        out[f"{n}.bias"] = (cout,)
+
+    def norm(n, c):
+        out[f"{n}.weight"] = (c,)
+        out[f"{n}.bias"] = (c,)
+
+    def resnet(n, cin, cout):
+        norm(f"{n}.norm1", cin); conv(f"{n}.conv1", cin, cout, 3); norm(f"{n}.norm2", cout); conv(f"{n}.conv2", cout, cout, 3)
+        if cin != cout:
+            conv(f"{n}.conv_shortcut", cin, cout, 1)
+
+    conv("encoder.conv_in", 3, VAE_BLOCK_OUT[0], 3)
+    prev = VAE_BLOCK_OUT[0]
+    for i, cout in enumerate(VAE_BLOCK_OUT):
+        for j in range(2):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+        if i < 3:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+        prev = cout
+    c = VAE_BLOCK_OUT[-1]
+    resnet("encoder.mid_block.resnets.0", c, c)
+    a = "encoder.mid_block.attentions.0"
+    norm(f"{a}.group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out[f"{a}.{n}.weight"] = (c, c)
+        out[f"{a}.{n}.bias"] = (c,)
+    resnet("encoder.mid_block.resnets.1", c, c)
+    norm("encoder.conv_norm_out", c); conv("encoder.conv_out", c, 8, 3); conv("quant_conv", 8, 8, 1)
+    return out
 
 
 def param_shapes() -> Dict[str, tuple]:

@@ -107,6 +107,13 @@ int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float*
                    void* y, int B, int H, int W, int Cin, int Cout, int stride, long long* chan_stats, int dtype,
                    void* stream);
 
+/* ---- diffusers Downsample2D(padding = 0) of the AutoencoderKL encoder: F.pad(x, (0, 1, 0, 1)) + conv3x3 stride 2
+ *  (zeros are added on the right / bottom only): y[B][H/2][W/2][Cout], H and W even.  chan_stats as in c2d_conv3x3_ex
+ *  (bf16 only, may be NULL).  SD-1.5 VAE encoder (third-party diffusers==0.23.1, requirements.txt:7; latent format
+ *  (4, 64, 64) per data/audiocaps_latent_v4.py:185). */
+int c2d_conv3x3_down(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int Cin, int Cout,
+                     long long* chan_stats, int dtype, int impl, void* stream);
+
 /* ---- per-channel statistics of x[B][HW][C] in the format above (for tensors not produced by an _ex call). */
 int c2d_channel_stats(const void* x, long long* chan_stats, int B, int HW, int C, int dtype, void* stream);
 

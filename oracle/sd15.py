@@ -157,6 +157,31 @@ def vae_decoder_spec() -> List[P]:
     return s
 
 
+def vae_encoder_spec() -> List[P]:
+    """AutoencoderKL encoder + quant_conv of SD-1.5 (diffusers==0.23.1 `Encoder`: in 3, block_out (128,256,512,512),
+    2 resnets per block, Downsample2D(padding=0) after blocks 0-2, mid block with one single-head attention,
+    double_z conv_out 512 -> 8).  34,163,592 + 72 parameters (with the decoder's 49,490,199: the 83,653,863 of the
+    published SD-1.5 VAE)."""
+    s = conv("encoder.conv_in", 3, VAE_BLOCK_OUT[0], 3)
+    prev = VAE_BLOCK_OUT[0]
+    for i, cout in enumerate(VAE_BLOCK_OUT):
+        for j in range(2):
+            s += _resnet_spec(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout, None)
+        if i < 3:
+            s += conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+        prev = cout
+    c = VAE_BLOCK_OUT[-1]
+    s += _resnet_spec("encoder.mid_block.resnets.0", c, c, None)
+    a = "encoder.mid_block.attentions.0"
+    s += norm(f"{a}.group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s += linear(f"{a}.{n}", c, c)
+    s += _resnet_spec("encoder.mid_block.resnets.1", c, c, None)
+    s += norm("encoder.conv_norm_out", c) + conv("encoder.conv_out", c, 8, 3)
+    s += conv("quant_conv", 8, 8, 1)
+    return s
+
+
 # =======================================================================================
 # Forward pieces
 # =======================================================================================
@@ -309,6 +334,30 @@ def vae_decode(sd, z):
             h = _conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", h)
     h = F.silu(_gn(sd, "decoder.conv_norm_out", h, 1e-6))
     return _conv(sd, "decoder.conv_out", h)
+
+
+def vae_encode(sd, img):
+    """AutoencoderKL.encode(img).latent_dist -> (mean, logvar), each [B,4,H/8,W/8]; the latent the pipeline stores is
+    `mean * 0.18215` (mode of the posterior; data/audiocaps_latent_v4.py:185 keeps (4,64,64) latents)."""
+    h = _conv(sd, "encoder.conv_in", img)
+    for i in range(4):
+        for j in range(2):
+            h = resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, None, eps=1e-6)
+        if i < 3:
+            h = F.pad(h, (0, 1, 0, 1))                                   # Downsample2D(padding=0): right / bottom only
+            h = _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=0)
+    h = resnet_block(sd, "encoder.mid_block.resnets.0", h, None, eps=1e-6)
+    a = "encoder.mid_block.attentions.0"
+    B, C, H, W = h.shape
+    hn = _gn(sd, f"{a}.group_norm", h, 1e-6).view(B, C, H * W).transpose(1, 2)
+    o = mha(_lin(sd, f"{a}.to_q", hn), _lin(sd, f"{a}.to_k", hn), _lin(sd, f"{a}.to_v", hn), 1)
+    o = _lin(sd, f"{a}.to_out.0", o).transpose(1, 2).reshape(B, C, H, W)
+    h = h + o
+    h = resnet_block(sd, "encoder.mid_block.resnets.1", h, None, eps=1e-6)
+    h = F.silu(_gn(sd, "encoder.conv_norm_out", h, 1e-6))
+    m = _conv(sd, "quant_conv", _conv(sd, "encoder.conv_out", h), padding=0)
+    mean, logvar = m[:, :4], m[:, 4:].clamp(-30.0, 20.0)
+    return mean, logvar
 
 
 # =======================================================================================

@@ -490,3 +490,21 @@ def test_xattn_strided_views_and_unsupported():
         ops.xattn(torch.zeros(1, 128, 320, device=DEV, dtype=F32), kv1, wq=w.float())
     with pytest.raises(Exception):
         ops.xattn_pack_kv(torch.zeros(1, 200, 640, device=DEV, dtype=BF16), heads)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 64, 128, 128), (2, 32, 256, 256), (1, 16, 512, 512), (3, 8, 24, 40), (16, 16, 512, 512)])
+def test_conv3x3_down_asymmetric_padding(B, H, Cin, Cout, dtype):
+    """diffusers Downsample2D(padding=0): zeros on the right / bottom only (c2d_conv3x3_down), incl. the split-K path."""
+    x = rnd(B, H, H, Cin, dtype=dtype)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), dtype)
+    b = rnd(Cout, seed=2)
+    y = ops.conv3x3_down(x, w, b)
+    assert tuple(y.shape) == (B, H // 2, H // 2, Cout)
+    assert rel(y, T.conv3x3_down(x, w, b)) < tol(dtype)
+    assert rel(y, T.conv3x3(x, w, b, stride=2)) > 1e-2          # NOT the symmetric pad-1 convolution
+    if dtype == BF16 and Cin % 8 == 0:
+        stats = torch.zeros(B * Cout * 2, device=DEV, dtype=torch.int64)
+        y2 = ops.conv3x3_down(x, w, b, stats=stats)
+        assert torch.equal(y2, y)
+        _stats_close(stats, y, B, Cout)

@@ -136,3 +136,25 @@ def test_inference_cli_end_to_end(tmp_path):
     assert im.size == (512, 512) and im.mode == "RGB"
     a = np.asarray(im).astype(np.float32)
     assert a.std() > 1.0            # not a constant image
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_vae_encoder_vs_oracle(dtype, tol):
+    """AutoencoderKL encoder on the GPU (Downsample2D through c2d_conv3x3_down on the tcgen05 / FFMA kernels) vs the
+    oracle restatement; encode -> decode keeps the image geometry."""
+    from clap2diffusion_b200.vae import VAEDecoder, VAEEncoder
+    from oracle.weights import synth_state_dict
+    from oracle.pipeline import np_randn, to_torch
+    sd = to_torch(synth_state_dict(sd15.vae_encoder_spec(), 3))
+    img = torch.tanh(torch.from_numpy(np_randn("vae_img", (2, 3, 128, 128))))
+    with torch.no_grad():
+        mean, logvar = sd15.vae_encode(sd, img)
+    enc = VAEEncoder(sd, device=DEV, dtype=dtype)
+    m2, lv2 = enc.moments(img.to(DEV))
+    z = enc.encode(img.to(DEV))
+    assert tuple(z.shape) == (2, 4, 16, 16) and z.dtype == torch.float32
+    assert PL.rel_l2(m2, mean) < tol and PL.rel_l2(lv2, logvar) < tol
+    assert PL.rel_l2(z, mean * sd15.VAE_SCALING) < tol
+    dsd = to_torch(synth_state_dict(sd15.vae_decoder_spec(), 0))
+    rec = VAEDecoder(dsd, device=DEV, dtype=dtype).decode(z)
+    assert tuple(rec.shape) == (2, 3, 128, 128) and torch.isfinite(rec).all()

@@ -301,6 +301,28 @@ def test_vae_host_logic_vs_oracle(W):
     assert rel_l2(img, ref) < 2e-5
 
 
+def test_vae_encoder_host_logic_vs_oracle():
+    """AutoencoderKL encoder: product launch sequence (Downsample2D as conv3x3_down, folded latent
+    scaling) == oracle restatement, and the state-dict contract (34,163,592 + 72 parameters)."""
+    from clap2diffusion_b200.vae import VAEEncoder, encoder_param_shapes
+    from oracle.weights import synth_state_dict
+    spec = sd15.vae_encoder_spec()
+    assert sum(int(np.prod(p.shape)) for p in spec) == 34_163_592 + 72
+    shapes = encoder_param_shapes()
+    assert {p.name: tuple(p.shape) for p in spec} == shapes
+    sd = to_torch(synth_state_dict(spec, 3))
+    img = torch.tanh(_t(np_randn("vae_img", (2, 3, 64, 64))))
+    with torch.no_grad():
+        mean, logvar = sd15.vae_encode(sd, img)
+    with torch_ops.installed(), torch.no_grad():
+        enc = VAEEncoder(sd, device="cpu", dtype=torch.float32)
+        m2, lv2 = enc.moments(img)
+        z = enc.encode(img)
+    assert tuple(z.shape) == (2, 4, 8, 8)
+    assert rel_l2(m2, mean) < 2e-5 and rel_l2(lv2, logvar) < 2e-5
+    assert rel_l2(z, mean * sd15.VAE_SCALING) < 2e-5
+
+
 def test_inference_cli_surface():
     """Same flags / defaults and class API as the reference's scripts/inference.py (:21-214)."""
     import ast

@@ -127,6 +127,15 @@ def conv3x3(x, w_packed, bias=None, *, rowvec=None, residual=None, stride=1, ups
     return y.contiguous().to(x.dtype)
 
 
+def conv3x3_down(x, w_packed, bias=None, *, out=None, impl=0, stats=None):
+    w = w_packed.float().permute(0, 3, 1, 2)
+    xin = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    y = F.conv2d(xin, w, None if bias is None else bias.float(), stride=2, padding=0).permute(0, 2, 3, 1)
+    if stats is not None:
+        _add_stats(stats, y, y.shape[0])
+    return y.to(x.dtype).contiguous()
+
+
 def group_norm(x, gamma, beta, groups=32, eps=1e-5, silu=False, *, x2=None, raw_cat=None, out=None):
     xx = x if x2 is None else torch.cat([x, x2], dim=-1)
     if raw_cat is not None:
