@@ -225,6 +225,21 @@ def run_kernels(args):
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
             tf = f"{a['flops'] / (a['ms'] * 1e-3) / 1e12:7.1f} TF/s" if a["flops"] else "            "
             print(f"  {k:18s} {a['ms']:8.3f} ms  {100 * a['ms'] / total:5.1f}%  x{a['launches']:<4d} {tf}  {a['bytes'] / (a['ms'] * 1e-3) / 1e9:8.1f} GB/s")
+        # AutoencoderKL encoder on the same kernels: 8 images 512x512 -> (4,64,64) latents
+        from clap2diffusion_b200 import synthetic as _syn
+        from clap2diffusion_b200.vae import VAEEncoder, encoder_param_shapes
+        enc = VAEEncoder(_syn.random_state_dict(encoder_param_shapes(), 1, dev), device=dev, dtype=torch.bfloat16)
+        img = torch.tanh(torch.randn(args.micro_batch, 3, 8 * LATENT, 8 * LATENT, device=dev))
+        for _ in range(2):
+            enc.encode(img)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            enc.encode(img)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"VAE encode ({args.micro_batch} images {8 * LATENT}x{8 * LATENT}): {e0.elapsed_time(e1) / 3:.3f} ms")
     agg = per_kernel_profile(pipe, args.micro_batch)
     total = sum(a["ms"] for a in agg.values())
     print(f"UNet step (batch {2 * args.micro_batch}) eager sum: {total:.3f} ms")
