@@ -45,7 +45,6 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 
 constexpr int XA_BM = 128, XA_BK = 64, XA_STAGES = 2, XA_THREADS = 192;
 constexpr int XA_A_BYTES = XA_BM * XA_BK * 2;
-constexpr int XA_MAX_NS = 112;          // 96 text(+concat) keys + 16 decoupled audio keys
 constexpr int XA_MAX_SLOTS = 3;
 
 struct XaParams {
@@ -543,7 +542,7 @@ static bool xa_plan(int C, int heads, int T, int T2, XaPlan& pl) {
     if (heads % g == 0 && g * pl.dp <= 256 && (g * pl.dp) % 32 == 0) { pl.G = g; break; }
   if (!pl.G) return false;
   pl.NG = pl.G * pl.dp;
-  if (T < 1 || T > 96 || T2 < 0 || T2 > 16) return false;
+  if (T < 1 || T > 96 || T2 < 0 || T2 > 16) return false;      // <= 96 text(+concat) keys + 16 decoupled audio keys = 7 chunks
   pl.s2 = (T + 15) & ~15;
   if (pl.s2 < 80) pl.s2 = 80;                  // kernel instances exist for 5, 6, 7 score chunks (columns >= T are masked)
   pl.NS = pl.s2 + (T2 ? 16 : 0);
