@@ -1138,6 +1138,16 @@ static bool use_persistent(bool geglu = false, int M = 0, int N = 0, int K = 0) 
   return m == 2 || (m == 0 && (geglu || (M >= 16384 && (K >= 640 || N >= 960))));
 }
 
+// C2D_SMALL_BN=0 keeps the small-M linears on the wide tiles (A/B runs)
+static bool small_bn_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_SMALL_BN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // tile width: widest tile that still yields at least one tile per SM, else 64 (more CTAs, deeper ring)
 static int pick_bn(int M, int N) {
   const int mt = ceil_div(M, TC_BM);
@@ -1170,8 +1180,12 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool ln_or_rs = lnx;       // these epilogues exist in the BN = 160 / 128 single-CTA kernels only
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
-  const int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                       : (geglu ? 128 : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+  int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
+                 : (geglu ? 128 : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+  // small M (the low-resolution levels, single-image latency): the wide tile leaves most SMs idle -> 64-column tiles
+  if (!pairk && !geglu && !persist && small_bn_enabled() && N % 64 == 0 &&
+      ceil_div(M, TC_BM) * ceil_div(N, BN) * 2 <= num_sms())
+    BN = 64;
   CUtensorMap tmA, tmA2, tmB;
   {
     uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
@@ -1224,6 +1238,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
       return launch_tc2<128, 5, false, false, true>(tmA, tmA2, tmB, p, s);
     }
     if (BN == 160) return launch_tc<160, false, false, true>(tmA, tmA2, tmB, p, s);
+    if (BN == 64) return launch_tc<64, false, false, true>(tmA, tmA2, tmB, p, s);
     return launch_tc<128, false, false, true>(tmA, tmA2, tmB, p, s);
   }
   if (persist) {
@@ -1234,6 +1249,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   }
   if (geglu) return launch_tc<128, false, true>(tmA, tmA2, tmB, p, s);
   if (BN == 160) return launch_tc<160, false, false>(tmA, tmA2, tmB, p, s);
+  if (BN == 64) return launch_tc<64, false, false>(tmA, tmA2, tmB, p, s);
   return launch_tc<128, false, false>(tmA, tmA2, tmB, p, s);
 }
 
