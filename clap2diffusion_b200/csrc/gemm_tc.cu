@@ -1035,28 +1035,31 @@ static int launch_tc3(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
 
 // ---- split-K: y = sum_z partial[z] + bias + rowvec[m / rows_per_vec] + residual -> bf16, plus the per-channel
 // fixed-point statistics the fused epilogue would have produced (integer atomics: order independent).
-// Block = 8 rows x (N / 8) column groups; thread = 8 consecutive columns of one row.
+// Block = SKF_ROWS row lanes x (N / 8) column groups; thread = 8 consecutive columns, `iters` rows (stride SKF_ROWS):
+// the column sums of a block's SKF_ROWS * iters rows cost ONE atomic pair per column (at M = 8192 a 4-row block spent
+// its time in 1.3 M atomics per convolution).
 constexpr int SKF_ROWS = 4;
 __global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ bias,
                                      const float* __restrict__ rowvec, int rows_per_vec, const bf16* __restrict__ residual,
                                      long long ldr, bf16* __restrict__ y, long long ldy, int M, int N,
-                                     unsigned long long* __restrict__ stats, int stats_rows) {
+                                     unsigned long long* __restrict__ stats, int stats_rows, int iters) {
   const int ng = N >> 3;
   const int g = threadIdx.x % ng, rsub = threadIdx.x / ng;
-  const int m = blockIdx.x * SKF_ROWS + rsub, n = g * 8;
-  float v[8];
+  const int n = g * 8;
+  const int row0 = blockIdx.x * SKF_ROWS * iters;
+  float b8[8], cs[8], cq[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  const bool ok = rsub < SKF_ROWS && m < M;
-  if (ok) {
+  for (int j = 0; j < 8; ++j) { b8[j] = bias ? __ldg(bias + n + j) : 0.f; cs[j] = 0.f; cq[j] = 0.f; }
+  for (int it = 0; it < iters; ++it) {
+    const int m = row0 + it * SKF_ROWS + rsub;
+    if (m >= M) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = b8[j];
     for (int z = 0; z < splits; ++z) {
       const float* src = partial + ((size_t)z * M + m) * N + n;
       const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-    }
-    if (bias) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + n + j);
     }
     if (rowvec) {
       const float* rv = rowvec + (size_t)(m / rows_per_vec) * N + n;
@@ -1070,17 +1073,17 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
       for (int j = 0; j < 8; ++j) v[j] += rr[j];
     }
     Vec8<bf16>::store(y + (size_t)m * ldy + n, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] = fmaf(v[j], v[j], cq[j]); }
   }
   if (stats) {
-    // column sums over the block's rows through shared memory (one pass per moment), then one atomic per column
+    // column sums over the block's row lanes through shared memory (one pass per moment), then one atomic per column
     __shared__ float sh[SKF_ROWS][1280 + 8];
-    const int bimg = (blockIdx.x * SKF_ROWS) / stats_rows;          // stats_rows % SKF_ROWS == 0: one image per block
+    const int bimg = row0 / stats_rows;                             // stats_rows % (SKF_ROWS * iters) == 0: one image per block
 #pragma unroll 1
     for (int kind = 0; kind < 2; ++kind) {
-      if (rsub < SKF_ROWS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sh[rsub][n + j] = ok ? (kind ? v[j] * v[j] : v[j]) : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) sh[rsub][n + j] = kind ? cq[j] : cs[j];
       __syncthreads();
       for (int col = threadIdx.x; col < N; col += blockDim.x) {
         float acc = 0.f;
@@ -1321,7 +1324,7 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
       splits = (2 * num_sms() + ctas - 1) / ctas;                   // aim at two CTAs per SM
       if (splits > 8) splits = 8;
       while (splits > 1 && (size_t)splits * p.M * Cout * sizeof(float) > SPLITK_WS_BYTES) --splits;
-      if (p.stats && p.stats_rows % SKF_ROWS) splits = 1;
+      if (p.stats_rows % SKF_ROWS) splits = 1;
     }
     if (splits > 1) {
       TcParams q = p;
@@ -1333,8 +1336,10 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
       if (rc) return rc;
       const int nsl = ceil_div(p.num_k_blocks, q.kb_per_split);
       const int threads = SKF_ROWS * (Cout / 8);
-      splitk_finish_kernel<<<ceil_div(p.M, SKF_ROWS), threads, 0, s>>>(ws, nsl, bias, rowvec, p.rows_per_vec, p.residual, p.ldr, p.y,
-                                                                      p.ldy, p.M, Cout, p.stats, p.stats_rows);
+      int iters = 1;                                     // rows per block = 4 * iters: ~two blocks per SM, <= 32 rows, one image
+      while (iters < 8 && ceil_div(p.M, SKF_ROWS * iters * 2) >= 2 * num_sms() && p.stats_rows % (SKF_ROWS * iters * 2) == 0) iters *= 2;
+      splitk_finish_kernel<<<ceil_div(p.M, SKF_ROWS * iters), threads, 0, s>>>(ws, nsl, bias, rowvec, p.rows_per_vec, p.residual, p.ldr,
+                                                                              p.y, p.ldy, p.M, Cout, p.stats, p.stats_rows, iters);
       return check_launch("conv3x3_tc");
     }
     if (BN == 256) return launch_tc3<256, 3, true, false>(tmA, tmA, tmB, p, s);
