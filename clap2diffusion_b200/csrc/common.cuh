@@ -179,6 +179,26 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may start -- barrier / TMEM set-up,
+// tensor-map prefetch, index arithmetic -- while the tail of its predecessor on the stream is still running; it must
+// call pdl_wait() before its FIRST global-memory access of any kind (inputs written by the predecessor, and outputs
+// whose buffer the predecessor may still be reading), and calls pdl_trigger() right after so that its own successor
+// may be scheduled as soon as all of this grid's CTAs are resident.  Without the launch attribute both are no-ops.
+// C2D_PDL=0 launches everything fully serialised (A/B runs).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // attention problem descriptor shared by the SIMT and tcgen05 attention kernels (see c2d_attention)
 struct AttnParams {
   const void *q, *k, *v;

@@ -230,6 +230,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();           // everything above overlapped the predecessor's tail; global memory is touched from here on
+  pdl_trigger();
 
   // Producer and MMA warps run their protocols CONVERGED and issue through elect_one(): the TMA / tcgen05
   // instructions are uniform-datapath instructions and must not sit in a lane-divergent region (tc_common.cuh).
@@ -463,7 +465,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
     attr_done = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM));
-  gemm_tc_kernel<BN, CONV, GEGLU, LNF><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
+  launch_pdl(gemm_tc_kernel<BN, CONV, GEGLU, LNF>, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -517,6 +519,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();           // everything above overlapped the predecessor's tail; global memory is touched from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer (runs ahead across tiles; converged warp, elected lane issues) =====================
@@ -739,7 +743,7 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   const int num_n = ceil_div(p.N, BN);
   const int num_tiles = num_n * ceil_div(p.M, TC_BM);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_tiles, num_n);
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p, num_tiles, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -800,6 +804,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                       // barrier inits and the TMEM allocation are visible to the peer CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; converged warp, elected lane issues) =====================
@@ -1029,7 +1035,7 @@ static int launch_tc3(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   const int num_n = ceil_div(p.N, BN);
   const int pairs = num_n * ceil_div(ceil_div(p.M, TC_BM), 2);
   const int splits = p.partial ? ceil_div(p.num_k_blocks, p.kb_per_split) : 1;
-  gemm_tc3_kernel<BN, STAGES, CONV, GEGLU><<<dim3(2 * pairs, splits), TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p, num_n);
+  launch_pdl(gemm_tc3_kernel<BN, STAGES, CONV, GEGLU>, dim3(2 * pairs, splits), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
 }
 
@@ -1043,6 +1049,8 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
                                      const float* __restrict__ rowvec, int rows_per_vec, const bf16* __restrict__ residual,
                                      long long ldr, bf16* __restrict__ y, long long ldy, int M, int N,
                                      unsigned long long* __restrict__ stats, int stats_rows, int iters) {
+  pdl_wait();
+  pdl_trigger();
   const int ng = N >> 3;
   const int g = threadIdx.x % ng, rsub = threadIdx.x / ng;
   const int n = g * 8;
@@ -1338,8 +1346,8 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
       const int threads = SKF_ROWS * (Cout / 8);
       int iters = 1;                                     // rows per block = 4 * iters: ~two blocks per SM, <= 32 rows, one image
       while (iters < 8 && ceil_div(p.M, SKF_ROWS * iters * 2) >= 2 * num_sms() && p.stats_rows % (SKF_ROWS * iters * 2) == 0) iters *= 2;
-      splitk_finish_kernel<<<ceil_div(p.M, SKF_ROWS * iters), threads, 0, s>>>(ws, nsl, bias, rowvec, p.rows_per_vec, p.residual, p.ldr,
-                                                                              p.y, p.ldy, p.M, Cout, p.stats, p.stats_rows, iters);
+      launch_pdl(splitk_finish_kernel, dim3(ceil_div(p.M, SKF_ROWS * iters)), dim3(threads), 0, s, (const float*)ws, nsl, bias, rowvec,
+                 p.rows_per_vec, p.residual, (long long)p.ldr, p.y, (long long)p.ldy, p.M, Cout, p.stats, p.stats_rows, iters);
       return check_launch("conv3x3_tc");
     }
     if (BN == 256) return launch_tc3<256, 3, true, false>(tmA, tmA, tmB, p, s);

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(GN2_MAX_THREADS, 2)
 gn_apply2_kernel(const T* __restrict__ x, const T* __restrict__ x2, const long long* __restrict__ st1,
                  const long long* __restrict__ st2, const float* __restrict__ gamma, const float* __restrict__ beta,
                  T* __restrict__ y, int HW, int C1, int C2, int groups, float eps, int silu, int rows_per_cta) {
+  pdl_wait();            // x and its statistics come from the kernel(s) just before this one
+  pdl_trigger();
   const int C = C1 + C2, nvec = C >> 3, cpg = C / groups;
   const int b = blockIdx.y;
   const int rif = blockDim.x / nvec;                    // rows in flight (blockDim is a multiple of nvec)
@@ -490,8 +492,8 @@ int c2d_group_norm_apply(const void* x, const void* x2, const long long* stats1,
   dim3 grid;
   int rpc;
   gn2_grid(B, HW, rif, &grid, &rpc);
-  gn_apply2_kernel<bf16><<<grid, threads, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)x2, stats1, stats2, gamma, beta,
-                                                                      (bf16*)y, HW, C1, C2, groups, eps, silu, rpc);
+  launch_pdl(gn_apply2_kernel<bf16>, grid, dim3(threads), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)x2, stats1, stats2, gamma,
+             beta, (bf16*)y, HW, C1, C2, groups, eps, silu, rpc);
   return check_launch("gn_apply");
 }
 

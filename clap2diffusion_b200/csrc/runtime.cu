@@ -1,5 +1,6 @@
 // Error plumbing, init, launch accounting for libc2d.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "common.cuh"
@@ -27,6 +28,15 @@ int check_launch(const char* what) {
     return C2D_ERR_CUDA;
   }
   return C2D_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int init_tc(int device);   // gemm_tc.cu
