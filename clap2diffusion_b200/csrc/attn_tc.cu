@@ -101,6 +101,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_o = tmem_base + AT_SB * AT_BK;
 
   // producer and MMA warps run converged and issue through elect_one() (see tc_common.cuh)
@@ -367,7 +369,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     attr_done = true;
   }
   dim3 grid(ceil_div(ap.Nq, AT_BQ), heads, B);
-  attn_tc_kernel<NBLK><<<grid, AT_THREADS, Cfg::SMEM_BYTES, s>>>(tq, tk, tv, ap);
+  launch_pdl(attn_tc_kernel<NBLK>, grid, dim3(AT_THREADS), (size_t)Cfg::SMEM_BYTES, s, tq, tk, tv, ap);
   return check_launch("attn_tc");
 }
 

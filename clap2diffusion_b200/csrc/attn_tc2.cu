@@ -183,6 +183,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -473,7 +475,7 @@ int attention_tc2(const AttnParams& p, int B, cudaStream_t s) {
       }                                                                                                            \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    attn_tc2_kernel<NP><<<grid, A2_THREADS, A2_SMEM, s>>>(tq, tk, tv, ap);                                         \
+    launch_pdl(attn_tc2_kernel<NP>, grid, dim3(A2_THREADS), (size_t)A2_SMEM, s, tq, tk, tv, ap);                    \
   } while (0)
   switch (poly) {
     case 0: A2_LAUNCH(0); break;

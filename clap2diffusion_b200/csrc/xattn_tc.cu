@@ -197,6 +197,7 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
     fence_barrier_init();
+    pdl_wait();           // x / row statistics come from the kernel just before this one
     // the first ring stages go out before the TMEM allocation and the CTA-wide sync: their latency overlaps the setup
     for (int kb = 0; kb < XA_STAGES && kb < p.num_kb; ++kb) {
       uint8_t* st = smem + kb * p.stage_bytes;
@@ -210,6 +211,8 @@ xattn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();             // (no-op for thread 0, which already waited) nothing above touches global memory
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -590,7 +593,7 @@ static int xa_launch(const CUtensorMap& tx, const CUtensorMap& tw, const XaParam
     }
     attr_bytes = smem_bytes;
   }
-  xattn_tc_kernel<NBLK, NCH><<<grid, XA_THREADS, smem_bytes, s>>>(tx, tw, p);
+  launch_pdl(xattn_tc_kernel<NBLK, NCH>, grid, dim3(XA_THREADS), (size_t)smem_bytes, s, tx, tw, p);
   return check_launch("xattn_tc");
 }
 
