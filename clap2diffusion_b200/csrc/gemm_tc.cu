@@ -765,8 +765,8 @@ struct Tc3Cfg {
   static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   static constexpr int EPI_PITCH = 36;                                          // floats per staged row (32 + pad)
   static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_PITCH * 4;           // aliases the pipeline stages
-  static constexpr int OFF_BIAS = STAGES * STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr int OFF_BIAS = STAGES * STAGE_BYTES;                         // bias[BN] then folded-LayerNorm column sums[BN]
+  static constexpr int OFF_BAR = OFF_BIAS + 2 * BN * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static_assert(EPI_BYTES <= STAGES * STAGE_BYTES, "epilogue staging must fit in the pipeline smem");
 };
@@ -876,15 +876,20 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const float* rv0 = rv_shared ? p.rowvec + (long long)(m0 / p.rows_per_vec) * p.N : nullptr;
       for (int j = threadIdx.x - 64; j < BN; j += 32 * TC_EPI_WARPS) {
         const int n = n0 + j;
-        float bv = 0.f;
+        float bv = 0.f, cs = 0.f;
         if (n < p.N) {
           if (p.bias) bv = __ldg(p.bias + n);
           if (rv0) bv += __ldg(rv0 + n);
+          if (p.ln_colsum) cs = __ldg(p.ln_colsum + n);
         }
         s_bias[j] = bv;
+        s_bias[BN + j] = cs;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
     }
+    // folded LayerNorm (GEGLU projection only in this kernel): y = rstd (acc - mean colsum) + bias
+    float ln_rstd = 1.f, ln_mr = 0.f;
+    if (GEGLU) ln_row_coeffs(p, m0 + q * 32 + lane, ln_rstd, ln_mr);
     mbar_wait(tmem_full, 0);      // all MMAs retired: the pipeline smem of BOTH CTAs is idle (staging aliases stage 0)
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -948,12 +953,17 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tmem_ld_32x32(t_row + grp * 128 + 64 + sub * 32, rg);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          v[j] = __uint_as_float(ra[j]) + s_bias[grp * 128 + sub * 32 + j];
-          v[j + 1] = __uint_as_float(ra[j + 1]) + s_bias[grp * 128 + sub * 32 + j + 1];
-          const float g0 = __uint_as_float(rg[j]) + s_bias[grp * 128 + 64 + sub * 32 + j];
-          const float g1 = __uint_as_float(rg[j + 1]) + s_bias[grp * 128 + 64 + sub * 32 + j + 1];
-          gelu_mul2(v[j], v[j + 1], g0, g1);
+        {
+          float gg[32];
+          if (p.ln_stats) {
+            epi_affine32<true>(ra, s_bias + grp * 128 + sub * 32, s_bias + BN + grp * 128 + sub * 32, ln_rstd, -ln_mr, v);
+            epi_affine32<true>(rg, s_bias + grp * 128 + 64 + sub * 32, s_bias + BN + grp * 128 + 64 + sub * 32, ln_rstd, -ln_mr, gg);
+          } else {
+            epi_affine32<false>(ra, s_bias + grp * 128 + sub * 32, s_bias, 1.f, 0.f, v);
+            epi_affine32<false>(rg, s_bias + grp * 128 + 64 + sub * 32, s_bias, 1.f, 0.f, gg);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) gelu_mul2(v[j], v[j + 1], gg[j], gg[j + 1]);
         }
       }
       float* srow = stage + (size_t)lane * Cfg::EPI_PITCH;
@@ -1142,6 +1152,14 @@ static int pick_bn_pair(int N) {
   if (N % 256 == 0) return 256;
   return 128;
 }
+static bool geglu_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_GEGLU_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 // auto: persistent for the GEGLU projection and for the large-M linears whose main loop is long enough (K >= 640)
 // or whose output is wide enough (N >= 960) for the cross-tile prefetch to pay (measured: -5 .. -16 %)
 static bool use_persistent(bool geglu = false, int M = 0, int N = 0, int K = 0) {
@@ -1187,7 +1205,11 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
     C2D_REQUIRE(!geglu && ex->stats_rows > 0 && ex->stats_rows % 32 == 0 && M % ex->stats_rows == 0,
                 "linear_tc: channel statistics need rows-per-image %% 32 == 0 (M=%d stats_rows=%d)", M, ex->stats_rows);
   const bool lnx = ex && (ex->ln_stats || ex->rowstats_out);      // only the single-CTA kernels carry these epilogues
-  const bool pairk = use_pair() && !lnx;
+  // C2D_GEGLU_PAIR=1: the GEGLU projection (with or without the folded LayerNorm) on CTA-pair 256 x 256 tiles, which
+  // halve the operand re-streaming from L2.  Measured on B200 (same box, UNet batch 16): 2.16-2.20 ms per step against
+  // 2.07-2.17 ms for the persistent single-CTA kernel (its cross-tile epilogue overlap is worth as much) -> off by default.
+  const bool geglu_pair = geglu && geglu_pair_enabled() && N % 256 == 0 && M >= 256 && !(ex && (ex->rowstats_out || ex->stats || ex->x2));
+  const bool pairk = (use_pair() && !lnx) || geglu_pair;
   const bool ln_or_rs = lnx;       // these epilogues exist in the BN = 160 / 128 single-CTA kernels only
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
