@@ -508,3 +508,37 @@ def test_conv3x3_down_asymmetric_padding(B, H, Cin, Cout, dtype):
         y2 = ops.conv3x3_down(x, w, b, stats=stats)
         assert torch.equal(y2, y)
         _stats_close(stats, y, B, Cout)
+
+
+def test_xattn_full_size_properties():
+    """BASELINE config-3 size (UNet batch 16, 4096 tokens, C = 320): size-independent properties of the fused kernel --
+    a softmax-weighted mean of constant values is that constant, permuting the keys changes nothing, a zero-weight
+    decoupled branch is the plain kernel, and the output is linear in V."""
+    B, Nq, C, Tk, heads = 16, 4096, 320, 77, 8
+    h = rnd(B * Nq, C, dtype=BF16).view(B, Nq, C)
+    w = rnd(C, C, dtype=BF16, scale=C ** -0.5, seed=1)
+    kv = rnd(B, Tk, 2 * C, dtype=BF16, seed=2)
+    # (a) V = per-column constants -> O = the same constants (probabilities sum to one)
+    cst = rnd(C, dtype=BF16, seed=3)
+    kvc = kv.clone()
+    kvc[..., C:] = cst
+    o = ops.xattn(h, ops.xattn_pack_kv(kvc, heads), wq=w)
+    assert float((o.float() - cst.float()).abs().max()) <= 2e-2 * float(cst.float().abs().max())
+    # (b) key permutation invariance
+    perm = torch.randperm(Tk, generator=torch.Generator().manual_seed(0)).to(DEV)
+    o1 = ops.xattn(h, ops.xattn_pack_kv(kv, heads), wq=w)
+    o2 = ops.xattn(h, ops.xattn_pack_kv(kv[:, perm].contiguous(), heads), wq=w)
+    assert rel(o2, o1) < 5e-3
+    # (c) a decoupled branch with weight 0 changes nothing (the 6-chunk instance sums the row in a different order: rounding only)
+    kv2 = rnd(B, 10, 2 * C, dtype=BF16, seed=4)
+    o3 = ops.xattn(h, ops.xattn_pack_kv(kv, heads, kv2, lambda2=0.0), wq=w)
+    assert rel(o3, o1) < 2e-3
+    # (d) linearity in V (the softmax does not depend on V)
+    kva, kvb = kv.clone(), kv.clone()
+    kvb[..., C:] = rnd(B, Tk, C, dtype=BF16, seed=5)
+    kvs = kv.clone()
+    kvs[..., C:] = (0.5 * kva[..., C:].float() + 0.25 * kvb[..., C:].float()).to(BF16)
+    oa = o1.float()
+    ob = ops.xattn(h, ops.xattn_pack_kv(kvb, heads), wq=w).float()
+    os_ = ops.xattn(h, ops.xattn_pack_kv(kvs, heads), wq=w).float()
+    assert rel(os_, 0.5 * oa + 0.25 * ob) < 1e-2
