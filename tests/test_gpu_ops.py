@@ -542,3 +542,20 @@ def test_xattn_full_size_properties():
     ob = ops.xattn(h, ops.xattn_pack_kv(kvb, heads), wq=w).float()
     os_ = ops.xattn(h, ops.xattn_pack_kv(kvs, heads), wq=w).float()
     assert rel(os_, 0.5 * oa + 0.25 * ob) < 1e-2
+
+
+def test_conv3x3_splitk_deterministic_and_linear():
+    """Split-K convolution at the benchmark batch (16 x 8 x 8, 1280 -> 1280): two runs are bit-identical (fixed slice
+    order, integer-atomic statistics) and the result is linear in the input."""
+    B, H, C = 16, 8, 1280
+    x1, x2 = rnd(B, H, H, C, dtype=BF16), rnd(B, H, H, C, dtype=BF16, seed=9)
+    w = ops.pack_conv3x3(rnd(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=1), BF16)
+    st1 = torch.zeros(B * C * 2, device=DEV, dtype=torch.int64)
+    st2 = torch.zeros_like(st1)
+    y1 = ops.conv3x3(x1, w, None, stats=st1)
+    y1b = ops.conv3x3(x1, w, None, stats=st2)
+    assert torch.equal(y1, y1b) and torch.equal(st1, st2)
+    y2 = ops.conv3x3(x2, w, None)
+    xs = (0.5 * x1.float() - 0.25 * x2.float()).to(BF16)
+    ys = ops.conv3x3(xs, w, None)
+    assert rel(ys, 0.5 * y1.float() - 0.25 * y2.float()) < 1e-2
