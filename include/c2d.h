@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 2
+#define C2D_ABI_VERSION 3   /* 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
 enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
 enum { C2D_F32 = 0, C2D_BF16 = 1 };
