@@ -194,6 +194,28 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   return make_tmap_bf16_strided(m, base, rank, dims, strides_bytes, box, nullptr);
 }
 
+// bf16 tensor map WITHOUT swizzle (dense shared-memory box: rows at box[0] * 2 bytes): TMA stores of epilogue tiles whose
+// rows are not a multiple of the 128-byte swizzle span.
+int make_tmap_bf16_plain(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box) {
+  int rc = get_encode();
+  if (rc) return rc;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (no swizzle) failed (CUresult %d): rank %d dims {%llu,%llu} stride0 %llu box {%u,%u} base %p",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0, base);
+    return C2D_ERR_CUDA;
+  }
+  return C2D_OK;
+}
+
 template <int BN>
 struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;

@@ -654,9 +654,17 @@ int xattn_pack_kv(const void* k, const void* v, long long ldkv, long long bskv, 
   return check_launch("xattn_pack_kv");
 }
 
+// xattn_tc2.cu: persistent weight-stationary kernel for the sites whose to_q slice fits in shared memory
+bool xattn_p_supported(int C, int heads, int Nq, int T, int T2);
+int xattn_p(const void* x, long long ldx, const void* wq, const float* qbias, const long long* ln_stats, const float* ln_colsum,
+            float ln_eps, const void* kv_packed, int T, void* o, long long ldo, int B, int Nq, int C, int heads, float scale,
+            cudaStream_t s);
+
 int xattn_tc(const void* x, long long ldx, const void* wq, const float* qbias, const long long* ln_stats,
              const float* ln_colsum, float ln_eps, const void* kv_packed, int T, int T2, float lambda2, void* o, long long ldo,
              int B, int Nq, int C, int heads, float scale, cudaStream_t s) {
+  if (xattn_p_supported(C, heads, Nq, T, T2))
+    return xattn_p(x, ldx, wq, qbias, ln_stats, ln_colsum, ln_eps, kv_packed, T, o, ldo, B, Nq, C, heads, scale, s);
   XaPlan pl;
   if (!xa_plan(C, heads, T, T2, pl) || !(Nq % XA_BM == 0 || (Nq < XA_BM && Nq % 32 == 0))) {
     set_error("xattn: shape outside the fused kernel (C=%d heads=%d Nq=%d T=%d T2=%d)", C, heads, Nq, T, T2);

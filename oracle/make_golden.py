@@ -247,12 +247,46 @@ def unet_goldens():
     print("unet goldens written")
 
 
+def full_trajectory_goldens():
+    """Oracle-generated (UNPINNED restatement, see oracle/__init__.py) full 50-step trajectories for the configurations
+    the benchmark numbers are quoted on (BASELINE.json configs[1], configs[2]):
+      * config 2: ONE image ("a beach", seed 0), 50 DDIM steps, CFG 7.5 -> all 50 per-step latents + decoded image;
+      * config 3: two more members of a micro-batch-8 prompt x seed sweep (slots 2 and 5 of `config3_jobs()`), 50 steps each.
+    The oracle treats every image independently (per-sample Norm-60, D3), so one image at a time is the batch's definition."""
+    import time
+    from oracle import pipeline as PL
+    torch.set_num_threads(os.cpu_count())
+    W = PL.build_weights(seed=0, with_vae=True)
+    ctx_u = torch.from_numpy(PL.text_states(""))[None]
+    t0 = time.time()
+    out = PL.sample(W, torch.from_numpy(PL.clap_embedding(0))[None], torch.from_numpy(PL.text_states("a beach"))[None], ctx_u,
+                    torch.from_numpy(PL.init_noise(0))[None], steps=50, guidance=7.5, decode=True)
+    print(f"  config2 (50 steps + decode) {time.time()-t0:.1f}s on {os.cpu_count()} cores")
+    np.savez_compressed(os.path.join(GOLD, "pipeline_cfg2_50steps.npz"), latents=torch.cat(out["latents"], 0).numpy(),
+                        image=out["image"].numpy().astype(np.float16))
+    jobs = PL.config3_jobs()
+    res = {}
+    for slot in (2, 5):
+        prompt, seed = jobs[slot]
+        t0 = time.time()
+        o = PL.sample(W, torch.from_numpy(PL.clap_embedding(seed))[None], torch.from_numpy(PL.text_states(prompt))[None], ctx_u,
+                      torch.from_numpy(PL.init_noise(seed))[None], steps=50, guidance=7.5)
+        print(f"  config3 slot {slot} ({prompt!r}, seed {seed}) {time.time()-t0:.1f}s")
+        res[f"latents_slot{slot}"] = torch.cat(o["latents"], 0).numpy()
+    np.savez_compressed(os.path.join(GOLD, "pipeline_cfg3_mb8_slots.npz"), slots=np.array([2, 5]), **res)
+    print("full-trajectory goldens written")
+
+
 if __name__ == "__main__":
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--unet", action="store_true")
     ap_.add_argument("--only-unet", action="store_true")
+    ap_.add_argument("--only-full", action="store_true", help="only the 50-step config-2 / config-3 trajectories")
     a = ap_.parse_args()
     sys.path.insert(0, ROOT)
+    if a.only_full:
+        full_trajectory_goldens()
+        sys.exit(0)
     if not a.only_unet:
         audio_goldens()
     if a.unet or a.only_unet:

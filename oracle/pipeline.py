@@ -56,6 +56,14 @@ def synthetic_audio(seed: int, n: int = 480000) -> np.ndarray:
     return a / (np.abs(a).max() + 1e-8)
 
 
+CONFIG3_PROMPTS = ("a beach", "a city street", "a forest", "a thunderstorm", "a cafe", "a train", "a river", "a crowd")
+
+
+def config3_jobs(n: int = 8, first_seed: int = 100):
+    """(prompt, seed) jobs of one micro-batch of the config-3 sweep (BASELINE.json configs[2]: 8 prompts x 8 seeds)."""
+    return [(CONFIG3_PROMPTS[j % len(CONFIG3_PROMPTS)], first_seed + j) for j in range(n)]
+
+
 # ---------------------------------------------------------------------------------------
 # weights
 # ---------------------------------------------------------------------------------------

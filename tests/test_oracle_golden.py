@@ -122,3 +122,74 @@ def test_unet_oracle_is_deterministic(gold):
     with torch.no_grad():
         eps = sd15.unet_forward(W["unet"], x, float(g["t"]), _t(PL.text_states("a beach"))[None], hook)
     assert rel_l2(eps, _t(g["eps"])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Known answers for the UNPINNED restatement (oracle/sd15.py: diffusers is absent, so these published /
+# definitional constants of SD-1.5 are what anchors it beyond the parameter counts).
+# ---------------------------------------------------------------------------------------------------------
+def test_sd15_scheduler_known_answers():
+    ac = sd15.alphas_cumprod()
+    assert len(ac) == 1000
+    assert abs(float(ac[0]) - 0.99915) < 1e-7                  # 1 - beta_start (scaled_linear 0.00085 .. 0.012)
+    assert abs(float(ac[999]) - 0.004660) < 5e-6               # SD-1.x terminal alpha-bar (published 0.00466)
+    sig = ((1 - ac) / ac) ** 0.5
+    assert abs(float(sig[999]) - 14.6146) < 1e-3               # EulerDiscrete sigma_max of SD-1.5
+    assert abs(float(sig[0]) - 0.0292) < 1e-4                  # sigma_min
+    # DDIM, eta 0, steps_offset 1, set_alpha_to_one False: the last step (t = 1) lands on alpha-bar[0], not on 1
+    t, ca, cb = sd15.ddim_coeffs(50)[-1]
+    assert t == 1
+    assert abs(ca - (float(ac[0]) / float(ac[1])) ** 0.5) < 1e-9
+    # x_prev = sqrt(a_p) x0 + sqrt(1 - a_p) eps with x0 = (x - sqrt(1 - a_t) eps) / sqrt(a_t), checked on numbers
+    a_t, a_p = float(ac[1]), float(ac[0])
+    x, e = 0.7, -0.3
+    x0 = (x - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+    assert abs(ca * x + cb * e - (a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * e)) < 1e-9
+    # Euler ('leading' spacing): first sigma of the 50-step plan is sigma(t = 981), sigmas end at 0
+    ts, sg = sd15.euler_sigmas(50)
+    assert ts[0] == 981.0 and sg[-1] == 0.0 and abs(sg[0] - float(sig[981])) < 1e-6
+    # CFG: uncond first, cond second; eps = eu + g (ec - eu)
+    e2 = torch.tensor([[1.0], [3.0]])
+    assert float(sd15.cfg_combine(e2, 7.5)) == 1.0 + 7.5 * 2.0
+    assert sd15.VAE_SCALING == 0.18215
+
+
+def test_sd15_timestep_embedding_order():
+    """flip_sin_to_cos=True, freq_shift=0 (SD-1.5 UNet config): [cos | sin], frequencies 10000^(-i/160)."""
+    e = sd15.timestep_embedding(torch.tensor([0.0, 1.0, 500.0]), 320)
+    assert e.shape == (3, 320)
+    assert torch.all(e[0, :160] == 1.0) and torch.all(e[0, 160:] == 0.0)
+    assert abs(float(e[1, 0]) - np.cos(1.0)) < 1e-6 and abs(float(e[1, 160]) - np.sin(1.0)) < 1e-6
+    assert abs(float(e[2, 80]) - np.cos(500.0 * 10000.0 ** (-0.5))) < 1e-4
+    assert abs(float(e[2, 160 + 159]) - np.sin(500.0 * 10000.0 ** (-159.0 / 160.0))) < 1e-5
+
+
+def test_sd15_geglu_chunk_order_and_block_wiring():
+    """GEGLU = value * gelu(gate) with value = FIRST half of the projection (diffusers GEGLU.forward), exact-erf GELU;
+    proj_in / proj_out are 1x1 convs around the block with the outer residual added after proj_out."""
+    C, name = 64, "t"
+    tb = f"{name}.transformer_blocks.0"
+    sd = {f"{name}.norm.weight": torch.ones(C), f"{name}.norm.bias": torch.zeros(C),
+          f"{name}.proj_in.weight": torch.zeros(C, C, 1, 1), f"{name}.proj_in.bias": torch.full((C,), 0.25),
+          f"{name}.proj_out.weight": torch.eye(C).reshape(C, C, 1, 1), f"{name}.proj_out.bias": torch.zeros(C)}
+    for n in ("norm1", "norm2", "norm3"):
+        sd[f"{tb}.{n}.weight"] = torch.ones(C)
+        sd[f"{tb}.{n}.bias"] = torch.zeros(C)
+    for a, kd in (("attn1", C), ("attn2", 768)):
+        sd[f"{tb}.{a}.to_q.weight"] = torch.zeros(C, C)
+        sd[f"{tb}.{a}.to_k.weight"] = torch.zeros(C, kd)
+        sd[f"{tb}.{a}.to_v.weight"] = torch.zeros(C, kd)
+        sd[f"{tb}.{a}.to_out.0.weight"] = torch.zeros(C, C)
+        sd[f"{tb}.{a}.to_out.0.bias"] = torch.zeros(C)
+    sd[f"{tb}.ff.net.0.proj.weight"] = torch.zeros(8 * C, C)
+    sd[f"{tb}.ff.net.0.proj.bias"] = torch.cat([torch.full((4 * C,), 2.0), torch.full((4 * C,), 1.0)])   # value 2, gate 1
+    w2 = torch.zeros(C, 4 * C)
+    w2[torch.arange(C), torch.arange(C)] = 1.0
+    sd[f"{tb}.ff.net.2.weight"] = w2
+    sd[f"{tb}.ff.net.2.bias"] = torch.zeros(C)
+    x = torch.zeros(1, C, 4, 4)
+    out = sd15.transformer_2d(sd, name, x, torch.zeros(1, 77, 768))
+    want = 0.25 + 2.0 * 0.5 * (1.0 + float(torch.erf(torch.tensor(1.0 / 2 ** 0.5))))       # 2 * gelu(1) = 1.68269
+    assert abs(want - 0.25 - 1.682689) < 1e-5
+    assert torch.allclose(out, torch.full_like(out, want), atol=1e-6)
+    assert abs(float(out[0, 0, 0, 0]) - (0.25 + 1.0 * 0.5 * (1.0 + float(torch.erf(torch.tensor(2.0 / 2 ** 0.5)))))) > 0.2  # swapped order would give gate*gelu(value)
