@@ -38,6 +38,9 @@ SIGNATURES = {
     "c2d_abi_version": [],
     "c2d_last_error": [],
     "c2d_init": [_i],
+    "c2d_destroy": [_i],
+    "c2d_splitk_workspace_bytes": [],
+    "c2d_set_workspace": [_i, _p, _ll],
     "c2d_launch_count": [],
     "c2d_last_kernel": [],
     "c2d_linear": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -85,7 +88,7 @@ SIGNATURES = {
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }
-_RESTYPES = {"c2d_xattn_packed_bytes": C.c_longlong, "c2d_last_error": C.c_char_p, "c2d_last_kernel": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
+_RESTYPES = {"c2d_xattn_packed_bytes": C.c_longlong, "c2d_splitk_workspace_bytes": C.c_longlong, "c2d_last_error": C.c_char_p, "c2d_last_kernel": C.c_char_p, "c2d_launch_count": C.c_ulonglong}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = symbol missing from the .so
@@ -104,13 +107,36 @@ def check(rc: int, what: str = "") -> None:
 
 
 _inited = set()
+_workspaces = {}          # device -> torch uint8 tensor registered with c2d_set_workspace (the CALLER owns the memory)
 
 
 def ensure_init(device: int) -> None:
-    """c2d_init once per device; raises C2DError when no sm_100 CUDA device is present."""
+    """c2d_init once per device; raises C2DError when no sm_100 CUDA device is present.  Also allocates (through
+    torch's allocator) and registers the split-K workspace: the library itself allocates nothing."""
     if device not in _inited:
         check(lib.c2d_init(int(device)), "c2d_init")
         _inited.add(device)
+        import torch
+        nbytes = int(lib.c2d_splitk_workspace_bytes())
+        set_workspace(device, torch.empty(nbytes, device=f"cuda:{int(device)}", dtype=torch.uint8))
+
+
+def set_workspace(device: int, ws) -> None:
+    """Register a caller-owned uint8 CUDA tensor as the device's split-K workspace (None removes it)."""
+    if ws is None:
+        check(lib.c2d_set_workspace(int(device), None, 0), "c2d_set_workspace")
+        _workspaces.pop(device, None)
+        return
+    assert ws.is_cuda and ws.is_contiguous() and ws.element_size() == 1
+    check(lib.c2d_set_workspace(int(device), ws.data_ptr(), ws.numel()), "c2d_set_workspace")
+    _workspaces[device] = ws
+
+
+def destroy(device: int) -> None:
+    """c2d_destroy + release of the workspace tensor; the next op on the device re-initialises."""
+    check(lib.c2d_destroy(int(device)), "c2d_destroy")
+    _workspaces.pop(device, None)
+    _inited.discard(device)
 
 
 def launch_count() -> int:

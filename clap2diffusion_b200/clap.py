@@ -34,8 +34,11 @@ DEPTHS, HEADS = (2, 2, 6, 2), (4, 8, 16, 32)
 HIDDEN, PROJ = 768, 512
 
 
-def _slaney_mel_filters() -> np.ndarray:
-    """[513, 64] triangular slaney-scale, area-normalised filters, 0 .. 14 kHz at 48 kHz (HF audio_utils.mel_filter_bank)."""
+def _slaney_mel_filters(frequency_min: float = 0.0, frequency_max: float = 14000.0) -> np.ndarray:
+    """[513, 64] triangular slaney-scale, area-normalised filters between frequency_min and frequency_max at 48 kHz
+    (HF audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney"), what ClapFeatureExtractor builds as
+    ``mel_filters_slaney`` from its ``frequency_min`` / ``frequency_max``).  The class defaults are 0 / 14000; the
+    ``laion/clap-htsat-unfused`` checkpoint's preprocessor_config.json sets frequency_min = 50."""
     nb = N_FFT // 2 + 1
     fft_freqs = np.linspace(0, SR // 2, nb)
 
@@ -47,7 +50,7 @@ def _slaney_mel_filters() -> np.ndarray:
         m = np.asarray(m, dtype=np.float64)
         return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
 
-    f = mel2hz(np.linspace(hz2mel(0.0), hz2mel(14000.0), N_MEL + 2))
+    f = mel2hz(np.linspace(hz2mel(float(frequency_min)), hz2mel(float(frequency_max)), N_MEL + 2))
     slopes = f[None, :] - fft_freqs[:, None]
     fb = np.maximum(0.0, np.minimum(-slopes[:, :-2] / np.diff(f)[:-1], slopes[:, 2:] / np.diff(f)[1:]))
     return fb * (2.0 / (f[2:] - f[:-2]))[None, :]
@@ -97,8 +100,12 @@ def param_shapes() -> Dict[str, tuple]:
 class ClapAudioTower:
     """``ClapAudioTower(state_dict, device, dtype)``: ``encode(waves fp32 [B, 480000]) -> fp32 [B, 512]`` (unit norm)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dtype=torch.bfloat16, clip_chunk: int = 16):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dtype=torch.bfloat16, clip_chunk: int = 16,
+                 frequency_min: float = 0.0, frequency_max: float = 14000.0):
+        """frequency_min / frequency_max: mel filter-bank range of the checkpoint's feature extractor
+        (preprocessor_config.json; ClapFeatureExtractor defaults 0 / 14000)."""
         self.device, self.dtype, self.clip_chunk = torch.device(device), dtype, int(clip_chunk)
+        self.frequency_min, self.frequency_max = float(frequency_min), float(frequency_max)
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}
         self._pack()
@@ -122,7 +129,7 @@ class ClapAudioTower:
         ang = 2.0 * np.pi * np.outer(k, n) / N_FFT
         w["window"] = torch.from_numpy(np.hanning(N_FFT + 1)[:-1].astype(np.float32)).to(dev)
         w["dft"] = torch.from_numpy(np.concatenate([np.cos(ang), np.sin(ang)], 0).astype(np.float32)).to(dev).contiguous()
-        w["mel_fb"] = torch.from_numpy(_slaney_mel_filters().T.astype(np.float32).copy()).to(dev).contiguous()    # [64, 513]
+        w["mel_fb"] = torch.from_numpy(_slaney_mel_filters(self.frequency_min, self.frequency_max).T.astype(np.float32).copy()).to(dev).contiguous()    # [64, 513]
         # eval-mode BatchNorm2d over mel bins folded into the dB kernel: y = dB * a + b
         g, b = self._f32(f"{e}.batch_norm.weight"), self._f32(f"{e}.batch_norm.bias")
         rm, rv = self._f32(f"{e}.batch_norm.running_mean"), self._f32(f"{e}.batch_norm.running_var")

@@ -114,9 +114,16 @@ int c2d_conv3x3_ex(const void* x, const void* w, const float* bias, const float*
                    int B, int H, int W, int Cin, int Cout, int stride, long long* chan_stats, int dtype, void* stream) {
   C2D_REQUIRE(x && w && y, "conv3x3_ex: null pointer");
   C2D_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_ex: bad dims");
-  C2D_REQUIRE(dtype == C2D_BF16 && conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
-              "conv3x3_ex: statistics-producing convolution exists on the tcgen05 (bf16) path only (H=%d W=%d Cin=%d)", H, W, Cin);
+  C2D_REQUIRE(dtype == C2D_BF16, "conv3x3_ex: the statistics-producing convolution exists on the bf16 path only");
+  C2D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0), "conv3x3_ex: stride 1, or 2 with even H, W");
   const int HWo = (H / stride) * (W / stride);
+  if (!conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0)) {
+    // planes the tcgen05 tiler does not take (output width neither a multiple of 128 nor a power of two, e.g. 64 x 96
+    // latents; Cin %% 8 != 0): the FFMA kernel + the stand-alone statistics pass -- slower, never silently wrong
+    int rc = conv3x3_simt(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, 0, dtype, (cudaStream_t)stream, 1);
+    if (rc || !chan_stats) return rc;
+    return c2d_channel_stats(y, chan_stats, B, HWo, Cout, dtype, stream);
+  }
   const bool fused = chan_stats && HWo % 32 == 0;
   int rc = conv3x3_tc(x, w, bias, rowvec, residual, y, B, H, W, Cin, Cout, stride, fused ? chan_stats : nullptr, (cudaStream_t)stream);
   if (rc || !chan_stats || fused) return rc;

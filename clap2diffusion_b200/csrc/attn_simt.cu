@@ -166,11 +166,8 @@ attn_simt_kernel(const AttnParams p) {
 template <typename T, int DJ>
 static int launch_attn(const AttnParams& p, int B, cudaStream_t s) {
   size_t smem = sizeof(float) * (2 * 64 * (p.d + 4) + 64 * 68);
-  static bool attr_done = false;   // per template instantiation
-  if (!attr_done) {
-    cudaFuncSetAttribute(attn_simt_kernel<T, DJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    attr_done = true;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};   // per template instantiation and device
+  if (int rc = ensure_dyn_smem(attn_simt_kernel<T, DJ>, 120 * 1024, smem_set, "attn_simt")) return rc;
   dim3 grid(ceil_div(p.Nq, FA_BQ), p.heads, B);
   attn_simt_kernel<T, DJ><<<grid, FA_THREADS, smem, s>>>(p);
   return check_launch("attn_simt");

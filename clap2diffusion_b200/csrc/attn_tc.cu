@@ -359,15 +359,8 @@ template <int NBLK>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& ap,
                           int heads, int B, cudaStream_t s) {
   using Cfg = AtCfg<NBLK>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("attention_tc: cudaFuncSetAttribute(%d B) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(attn_tc_kernel<NBLK>, Cfg::SMEM_BYTES, smem_set, "attention_tc")) return rc;
   dim3 grid(ceil_div(ap.Nq, AT_BQ), heads, B);
   launch_pdl(attn_tc_kernel<NBLK>, grid, dim3(AT_THREADS), (size_t)Cfg::SMEM_BYTES, s, tq, tk, tv, ap);
   return check_launch("attn_tc");

@@ -466,15 +466,8 @@ int attention_tc2(const AttnParams& p, int B, cudaStream_t s) {
   dim3 grid(ceil_div(p.Nq, A2_BQ * A2_QT), p.heads, B);
 #define A2_LAUNCH(NP)                                                                                              \
   do {                                                                                                             \
-    static bool attr_done = false;                                                                                 \
-    if (!attr_done) {                                                                                              \
-      cudaError_t e = cudaFuncSetAttribute(attn_tc2_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM); \
-      if (e != cudaSuccess) {                                                                                      \
-        set_error("attention_tc2: cudaFuncSetAttribute(%d B) failed: %s", A2_SMEM, cudaGetErrorString(e));         \
-        return C2D_ERR_CUDA;                                                                                       \
-      }                                                                                                            \
-      attr_done = true;                                                                                            \
-    }                                                                                                              \
+    static int smem_set[C2D_MAX_DEVICES] = {};                                                                     \
+    if (int rc = ensure_dyn_smem(attn_tc2_kernel<NP>, A2_SMEM, smem_set, "attention_tc2")) return rc;              \
     launch_pdl(attn_tc2_kernel<NP>, grid, dim3(A2_THREADS), (size_t)A2_SMEM, s, tq, tk, tv, ap);                    \
   } while (0)
   switch (poly) {

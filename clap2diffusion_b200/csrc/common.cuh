@@ -221,16 +221,27 @@ struct GemmExtras {
   float ln_eps;
 };
 
-static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-static inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+// ---- per-device state.  The library keeps NO process-global mutable compute state: what it remembers (largest
+// dynamic-smem size set per kernel instantiation, the caller-provided split-K workspace, the SM count) is per device.
+constexpr int C2D_MAX_DEVICES = 16;
+int cur_device();                      // runtime.cu: cudaGetDevice clamped to [0, C2D_MAX_DEVICES)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: `set_bytes` (one static array per
+// kernel instantiation) remembers the largest size already granted on each device.
+template <typename K>
+static inline int ensure_dyn_smem(K kern, int bytes, int (&set_bytes)[C2D_MAX_DEVICES], const char* what) {
+  const int dev = cur_device();
+  if (bytes <= set_bytes[dev]) return C2D_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cudaFuncSetAttribute(%d B dynamic smem) failed on device %d: %s", what, bytes, dev, cudaGetErrorString(e));
+    return C2D_ERR_CUDA;
   }
-  return n;
+  set_bytes[dev] = bytes;
+  return C2D_OK;
 }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+int num_sms();                         // runtime.cu: SM count of the CURRENT device (cached per device)
 
 }  // namespace c2d

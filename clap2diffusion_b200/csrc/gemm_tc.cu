@@ -476,16 +476,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, bool CONV, bool GEGLU, bool LNF = false>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = TcCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CONV, GEGLU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(gemm_tc_kernel<BN, CONV, GEGLU, LNF>, Cfg::SMEM_BYTES, smem_set, "gemm_tc")) return rc;
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM));
   launch_pdl(gemm_tc_kernel<BN, CONV, GEGLU, LNF>, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
@@ -752,16 +744,8 @@ template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF = false>
 static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = Tc2Cfg<BN, STAGES>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "persistent GEMM smem");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc2: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF>, Cfg::SMEM_BYTES, smem_set, "gemm_tc2")) return rc;
   const int num_n = ceil_div(p.N, BN);
   const int num_tiles = num_n * ceil_div(p.M, TC_BM);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
@@ -1054,16 +1038,8 @@ template <int BN, int STAGES, bool CONV, bool GEGLU>
 static int launch_tc3(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
   using Cfg = Tc3Cfg<BN, STAGES>;
   static_assert(Cfg::SMEM_BYTES <= 113 * 1024, "two CTAs per SM");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<BN, STAGES, CONV, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("gemm_tc3: cudaFuncSetAttribute(%d B smem) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_done = true;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(gemm_tc3_kernel<BN, STAGES, CONV, GEGLU>, Cfg::SMEM_BYTES, smem_set, "gemm_tc3")) return rc;
   const int num_n = ceil_div(p.N, BN);
   const int pairs = num_n * ceil_div(ceil_div(p.M, TC_BM), 2);
   const int splits = p.partial ? ceil_div(p.num_k_blocks, p.kb_per_split) : 1;
@@ -1136,14 +1112,10 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
   }
 }
 
-// per-device split-K workspace (allocated once at c2d_init; see conv3x3_tc)
-static float* g_splitk_ws[16] = {};
-constexpr size_t SPLITK_WS_BYTES = (size_t)32 << 20;
-static float* splitk_workspace() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  return (dev >= 0 && dev < 16) ? g_splitk_ws[dev] : nullptr;
-}
+// Split-K workspace: CALLER-owned (c2d_set_workspace), one per device; the library allocates nothing.  Without a
+// workspace the small-plane convolutions simply stay un-split.
+constexpr size_t SPLITK_WS_BYTES = (size_t)32 << 20;       // c2d_splitk_workspace_bytes(): fp32 slices of the largest split
+float* splitk_workspace(size_t* bytes);                   // runtime.cu (per-device context)
 
 // Kernel selection.  Measured on B200 (tools/bench_shapes.py): the persistent kernel wins on the GEGLU projection
 // (N = 8C, short K: +20 %), the two-CTA-per-SM kernel wins elsewhere (two MMA issuers hide each other's
@@ -1324,14 +1296,20 @@ bool conv3x3_tc_supported(const void* x, const void* w, int B, int H, int W, int
   if (up || (stride != 1 && stride != 2)) return false;
   if (stride == 2 && ((H & 1) || (W & 1))) return false;
   const int Ho = H / stride, Wo = W / stride;
-  return Cin % 8 == 0 && Cin >= 8 && Cout >= 1 && is_pow2(Wo) && is_pow2(Ho) && al16(x) && al16(w) &&
-         ((long long)Ho * Wo >= 128 || 128 % (Ho * Wo) == 0) && (stride == 1 || Wo <= 128);
+  // a tile is 128 consecutive output pixels in raster order and must be ONE TMA box (bw x bh x bb): whole multiples of
+  // 128 columns, or rows of a power-of-two width <= 64 stacked 128 / Wo high (Ho a multiple of that), or whole small
+  // planes (Ho * Wo dividing 128).  Ho itself need not be a power of two (e.g. 96 x 64 latents of a 768 x 512 image).
+  bool geom;
+  if (Wo >= 128) geom = Wo % 128 == 0;
+  else if (128 % Wo) geom = false;
+  else geom = Ho >= 128 / Wo ? Ho % (128 / Wo) == 0 : 128 % (Ho * Wo) == 0;
+  return Cin % 8 == 0 && Cin >= 8 && Cout >= 1 && geom && al16(x) && al16(w) && (stride == 1 || Wo <= 128);
 }
 
 int conv3x3_tc(const void* x, const void* w, const float* bias, const float* rowvec, const void* residual, void* y, int B,
                int H, int W, int Cin, int Cout, int stride, long long* stats, cudaStream_t s, int pad) {
   C2D_REQUIRE(conv3x3_tc_supported(x, w, B, H, W, Cin, Cout, stride, 0),
-              "conv3x3_tc: needs stride 1|2, pow2 output H/W, Cin %% 8 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
+              "conv3x3_tc: needs stride 1|2, output rows that tile into 128-pixel boxes, Cin %% 8 == 0 (H=%d W=%d Cin=%d Cout=%d)", H, W, Cin, Cout);
   const int Ho = H / stride, Wo = W / stride;
   const int bw = Wo < 128 ? Wo : 128;
   const int bh = (128 / bw) < Ho ? (128 / bw) : Ho;
@@ -1370,12 +1348,13 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
     // Small planes (8x8 latents: M = B * 64): the tile grid does not fill the machine while K = 9 Cin is long ->
     // split the reduction over blockIdx.y (fp32 slices in the per-device workspace + one finishing pass).
     const int ctas = 2 * ceil_div(Cout, BN) * ceil_div(ceil_div(p.M, TC_BM), 2);
-    float* ws = splitk_workspace();
+    size_t ws_bytes = 0;
+    float* ws = splitk_workspace(&ws_bytes);
     int splits = 1;
     if (splitk_enabled() && ws && ctas * 2 <= num_sms() * 2 && Cout % 8 == 0 && Cout <= 1280 && p.num_k_blocks >= 32) {
       splits = (2 * num_sms() + ctas - 1) / ctas;                   // aim at two CTAs per SM
       if (splits > 8) splits = 8;
-      while (splits > 1 && (size_t)splits * p.M * Cout * sizeof(float) > SPLITK_WS_BYTES) --splits;
+      while (splits > 1 && (size_t)splits * p.M * Cout * sizeof(float) > ws_bytes) --splits;
       if (p.stats_rows % SKF_ROWS) splits = 1;
     }
     if (splits > 1) {
@@ -1407,12 +1386,10 @@ int conv3x3_tc(const void* x, const void* w, const float* bias, const float* row
   return launch_tc<128, true, false>(tmA, tmA, tmB, p, s);
 }
 
+long long splitk_workspace_bytes() { return (long long)SPLITK_WS_BYTES; }
+
 int init_tc(int device) {
-  if (device >= 0 && device < 16 && !g_splitk_ws[device]) {
-    void* ws = nullptr;
-    if (cudaMalloc(&ws, SPLITK_WS_BYTES) == cudaSuccess) g_splitk_ws[device] = reinterpret_cast<float*>(ws);
-    else cudaGetLastError();          // no workspace: the small-M convolutions simply stay un-split
-  }
+  (void)device;
   return get_encode();
 }
 

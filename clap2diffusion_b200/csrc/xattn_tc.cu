@@ -584,15 +584,8 @@ bool xattn_tc_supported(int C, int heads, int Nq, int T, int T2) {
 
 template <int NBLK, int NCH>
 static int xa_launch(const CUtensorMap& tx, const CUtensorMap& tw, const XaParams& p, int smem_bytes, dim3 grid, cudaStream_t s) {
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_tc_kernel<NBLK, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) {
-      set_error("xattn_tc: cudaFuncSetAttribute(%d B) failed: %s", smem_bytes, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_bytes = smem_bytes;
-  }
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(xattn_tc_kernel<NBLK, NCH>, smem_bytes, smem_set, "xattn_tc")) return rc;
   launch_pdl(xattn_tc_kernel<NBLK, NCH>, grid, dim3(XA_THREADS), (size_t)smem_bytes, s, tx, tw, p);
   return check_launch("xattn_tc");
 }

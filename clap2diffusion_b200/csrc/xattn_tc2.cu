@@ -719,15 +719,8 @@ int xattn_p(const void* x, long long ldx, const void* wq, const float* qbias, co
   const int want = p.n_tiles * p.ngroups;
   if (ctas > want) ctas = want;
   auto kern = poly ? xattn_p_kernel<5, true> : xattn_p_kernel<5, false>;
-  static int attr_bytes[2] = {0, 0};
-  if (pl.smem_bytes > attr_bytes[poly]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
-    if (e != cudaSuccess) {
-      set_error("xattn_p: cudaFuncSetAttribute(%d B) failed: %s", pl.smem_bytes, cudaGetErrorString(e));
-      return C2D_ERR_CUDA;
-    }
-    attr_bytes[poly] = pl.smem_bytes;
-  }
+  static int smem_set[2][C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(kern, pl.smem_bytes, smem_set[poly], "xattn_p")) return rc;
   launch_pdl(kern, dim3((unsigned)ctas), dim3(XP_THREADS), (size_t)pl.smem_bytes, s, tx, tw, to, p);
   return check_launch("xattn_p");
 }

@@ -15,6 +15,12 @@ What differs from the reference (by design, results identical):
   * the audio injection + K/V projections are step-invariant, so they are exposed separately
     (``prepare`` -> cached K/V, ``attend`` -> per-step work); ``__call__`` = prepare + attend;
   * attention probabilities are never materialised (flash kernel), no head permutes;
+  * the stand-alone ``__call__`` (the path a real diffusers UNet takes) keeps the projected / packed K/V of a site in
+    a small identity-keyed cache: a denoising loop passes the SAME ``encoder_hidden_states`` / audio tensors every
+    step, so K/V are projected once per image there too (any in-place change bumps ``_version`` and misses);
+  * ``attention_mask`` (reference :129 hands it to ``attn.get_attention_scores``, i.e. an additive bias): key-padding
+    masks -- boolean, or additive 0 / -inf of shape [B,T], [B,1,T] or [B*heads,1,T] -- are honoured; a bias that
+    differs per head or per query row raises ``C2DError`` (no kernel for it, never silently ignored);
   * CUDA only -- a CPU tensor raises ``C2DError`` (no fallback).
 """
 from __future__ import annotations
@@ -71,6 +77,7 @@ class AudioAttnProcessor(nn.Module):
                                         nn.Linear(bottleneck_dim, hidden_dim))
         self.alpha = nn.Parameter(torch.zeros(1))
         self._cache = _CastCache()
+        self._kv_cache: Dict[int, Any] = {}      # id(attn) -> (identity key, K/V) of the last stand-alone call
 
     # ---- step-invariant part -------------------------------------------------------------------
     def context(self, encoder_hidden_states: torch.Tensor, audio_tokens: Optional[torch.Tensor]) -> torch.Tensor:
@@ -130,13 +137,17 @@ class AudioAttnProcessor(nn.Module):
 
     def attend(self, attn, hidden_states: torch.Tensor, kv, residual: Optional[torch.Tensor] = None,
                scale: float = 1.0, ln_stats: Optional[torch.Tensor] = None,
-               row_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+               row_stats: Optional[torch.Tensor] = None, key_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """to_q -> softmax(q k^T d^-1/2) v -> to_out[0] (+ residual).  hidden_states [B,N,C].
         ln_stats: the engine's LayerNorm-free mode -- hidden_states is the un-normalised residual stream, norm2 is
         folded into the to_q GEMM (attn.ln_q, prepared by SD15UNet); row_stats: statistics accumulator of the output."""
         dt = hidden_states.dtype
         c = self._cache
         out_lin = _to_out_linear(attn)
+        if key_mask is not None and isinstance(kv, ops.XattnKV):
+            if kv.kv is None:
+                raise C2DError("attention_mask with mode='decoupled' is not supported")
+            kv = kv.kv                       # masked keys: the flash kernel with a key mask (the fused kernel has none)
         if isinstance(kv, ops.XattnKV) and not ops.xattn_supported(hidden_states, attn.heads, kv.T, kv.T2):
             if kv.kv is None:
                 raise C2DError(f"mode='decoupled' needs the fused kernel; {hidden_states.shape[1]} tokens per sample is "
@@ -157,9 +168,65 @@ class AudioAttnProcessor(nn.Module):
         else:
             q = ops.linear(hidden_states, c.get(_weight(attn.to_q), dt, ("wq", id(attn))))
         d = C // attn.heads
-        o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=float(getattr(attn, "scale", d ** -0.5)) * scale)
+        o = ops.attention(q, kv[..., :C], kv[..., C:], attn.heads, scale=float(getattr(attn, "scale", d ** -0.5)) * scale,
+                          mask=key_mask)
         bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
         return ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias, residual=residual, row_stats=row_stats)
+
+    # ---- attention_mask (reference :129) ------------------------------------------------------
+    @staticmethod
+    def _key_mask(attention_mask: torch.Tensor, B: int, heads: int, T: int) -> torch.Tensor:
+        """Reduce diffusers' attention mask (additive bias added to q k^T, or boolean keep-mask) to a uint8 [B,T] key
+        mask.  Raises when the bias is not a pure key-padding mask."""
+        m = attention_mask
+        if m.dim() == 2:
+            m = m[:, None, :]
+        if m.dim() != 3 or m.shape[-1] != T:
+            raise C2DError(f"attention_mask of shape {tuple(attention_mask.shape)} does not match {T} keys")
+        if m.shape[1] != 1:
+            if not bool((m == m[:, :1]).all()):
+                raise C2DError("attention_mask differs per query row: only key-padding masks are supported")
+            m = m[:, :1]
+        if m.shape[0] == B * heads:
+            mh = m.reshape(B, heads, 1, T)
+            if not bool((mh == mh[:, :1]).all()):
+                raise C2DError("attention_mask differs per head: only key-padding masks are supported")
+            m = mh[:, 0]
+        elif m.shape[0] != B:
+            raise C2DError(f"attention_mask batch {m.shape[0]} is neither B={B} nor B*heads={B * heads}")
+        m = m.reshape(B, T)
+        if m.dtype == torch.bool:
+            keep = m
+        else:
+            mf = m.float()
+            keep = mf > -1e4
+            if not bool(((mf == 0) | ~keep).all()):
+                raise C2DError("attention_mask is a general additive bias: only 0 / -inf key-padding masks are supported")
+        if not bool(keep.any(dim=1).all()):
+            raise C2DError("attention_mask removes every key of a sample")
+        return keep.to(torch.uint8).contiguous()
+
+    def _cached_kv(self, attn, x: torch.Tensor, ehs: torch.Tensor, audio, pack: bool):
+        """K/V of a site for the stand-alone call, reused while the inputs are the same tensors (same storage and
+        version counters) -- what a denoising loop over a diffusers UNet passes at every step."""
+        tokens = audio.get(self.level) if isinstance(audio, dict) else None
+        params = [self.alpha, self.audio_proj[0].weight, self.audio_proj[0].bias, self.audio_proj[3].weight,
+                  self.audio_proj[3].bias, _weight(attn.to_k), _weight(attn.to_v)]
+        ident = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), ehs.dtype, x.dtype,
+                 None if tokens is None else (tokens.data_ptr(), tokens._version, tuple(tokens.shape), tokens.dtype),
+                 self.mode, pack, tuple((t.data_ptr(), t._version) for t in params))
+        hit = self._kv_cache.get(id(attn))
+        if hit is not None and hit[0] == ident:
+            return hit[1]
+        e = ehs if ehs.dtype == x.dtype else ops.cast(ehs.contiguous(), x.dtype)
+        kv = self.prepare(attn, e, audio)
+        self.kv_projections = getattr(self, "kv_projections", 0) + 1     # how often K/V were actually (re)computed
+        if pack and torch.is_tensor(kv) and ops.xattn_supported(x, attn.heads, kv.shape[1]) and ops.xattn_packable(
+                x.shape[-1], attn.heads, kv.shape[1], x.dtype):
+            kv = ops.xattn_pack_kv(kv, attn.heads)       # bf16, SD-1.5 shapes: to_q + attention core in one kernel
+        # keep the source tensors alive next to the entry: a freed-and-reused address must not look like a hit
+        self._kv_cache[id(attn)] = (ident, kv, ehs, tokens)
+        return kv
 
     # ---- diffusers processor protocol ----------------------------------------------------------
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
@@ -169,8 +236,6 @@ class AudioAttnProcessor(nn.Module):
             raise C2DError("AudioAttnProcessor runs on CUDA only (libc2d has no CPU path)")
         if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "norm_cross", None):
             raise C2DError("spatial_norm / norm_cross attention variants are not on the SD-1.5 path")
-        if attention_mask is not None:
-            raise C2DError("attention_mask is not supported (always None on the SD-1.5 path)")
         x = hidden_states
         nd = x.dim()
         if nd == 4:                                   # [B,C,H,W] -> [B,HW,C]   (reference :67-70)
@@ -186,20 +251,19 @@ class AudioAttnProcessor(nn.Module):
                 raise C2DError("scale != 1 with encoder_hidden_states=None is not supported")
             k = ops.linear(q, c.get(_weight(attn.to_k), dt, ("wk", id(attn))))
             v = ops.linear(q, c.get(_weight(attn.to_v), dt, ("wv", id(attn))))
-            o = ops.attention(q, k, v, attn.heads, scale=float(getattr(attn, "scale", (q.shape[-1] // attn.heads) ** -0.5)))
+            km = None if attention_mask is None else self._key_mask(attention_mask, q.shape[0], attn.heads, k.shape[1])
+            o = ops.attention(q, k, v, attn.heads, scale=float(getattr(attn, "scale", (q.shape[-1] // attn.heads) ** -0.5)), mask=km)
             out_lin = _to_out_linear(attn)
             bias = None if out_lin.bias is None else c.get(out_lin.bias, torch.float32, ("bo", id(attn)))
             out = ops.linear(o, c.get(out_lin.weight, dt, ("wo", id(attn))), bias)
         else:
-            ehs = encoder_hidden_states
-            if ehs.dtype != x.dtype:
-                ehs = ops.cast(ehs.contiguous(), x.dtype)
-            kv = self.prepare(attn, ehs, cross_attention_kwargs.get("audio"))
-            if torch.is_tensor(kv) and ops.xattn_supported(x, attn.heads, kv.shape[1]) and ops.xattn_packable(
-                    x.shape[-1], attn.heads, kv.shape[1], x.dtype):
-                kv = ops.xattn_pack_kv(kv, attn.heads)       # bf16, SD-1.5 shapes: to_q + attention core in one kernel
+            kv = self._cached_kv(attn, x, encoder_hidden_states, cross_attention_kwargs.get("audio"), pack=attention_mask is None)
+            km = None
+            if attention_mask is not None:
+                T = kv.T if isinstance(kv, ops.XattnKV) else kv.shape[1]
+                km = self._key_mask(attention_mask, x.shape[0], attn.heads, T)
             res = x if getattr(attn, "residual_connection", False) and nd != 4 else None
-            out = self.attend(attn, x, kv, residual=res, scale=scale)
+            out = self.attend(attn, x, kv, residual=res, scale=scale, key_mask=km)
         if nd == 4:                                   # back to [B,C,H,W] (reference :137-138)
             out = ops.transpose(out).reshape(B, Cc, H, W)
             if getattr(attn, "residual_connection", False):

@@ -30,7 +30,12 @@ class CLAPAudioEncoder(nn.Module):
 
     def __init__(self, model_name: str = "laion/clap-htsat-unfused", sample_rate: int = 48000, target_length: float = 10.0,
                  device: str = "cuda", freeze: bool = False, state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 dtype: torch.dtype = torch.bfloat16):
+                 dtype: torch.dtype = torch.bfloat16, feature_config: Optional[Dict[str, float]] = None):
+        """feature_config: the checkpoint's feature-extractor settings (``frequency_min``, ``frequency_max``,
+        ``truncation``, ``padding``) -- the reference gets them from ``ClapProcessor.from_pretrained(model_name)``
+        (:47), i.e. from preprocessor_config.json.  Default: that file when it can be found (model directory or the
+        local HF cache), else the values ``laion/clap-htsat-*`` checkpoints publish (frequency_min 50, frequency_max
+        14000, rand_trunc / repeatpad), else the ClapFeatureExtractor class defaults."""
         super().__init__()
         self.model_name = model_name
         self.sample_rate = sample_rate
@@ -41,11 +46,43 @@ class CLAPAudioEncoder(nn.Module):
         missing = set(param_shapes()) - set(state_dict)
         if missing:
             raise KeyError(f"CLAP state dict lacks {len(missing)} tensors, e.g. {sorted(missing)[0]}")
-        self.tower = ClapAudioTower(state_dict, device=device, dtype=dtype)
+        self.feature_config = self._feature_config(model_name, feature_config)
+        if self.feature_config.get("truncation", "rand_trunc") != "rand_trunc" or self.feature_config.get("padding", "repeatpad") != "repeatpad":
+            raise C2DError(f"feature extractor mode {self.feature_config} is not the unfused rand_trunc / repeatpad path")
+        self.tower = ClapAudioTower(state_dict, device=device, dtype=dtype,
+                                    frequency_min=self.feature_config["frequency_min"],
+                                    frequency_max=self.feature_config["frequency_max"])
         self.embedding_dim = 512
         self._frozen = True          # inference engine: the tower holds packed, non-trainable weights
         if freeze:
             self.freeze_encoder()
+
+    @staticmethod
+    def _feature_config(model_name: str, given: Optional[Dict[str, float]]) -> Dict[str, float]:
+        import json
+        import os
+        cfg = {"frequency_min": 0.0, "frequency_max": 14000.0, "truncation": "rand_trunc", "padding": "repeatpad", "source": "ClapFeatureExtractor defaults"}
+        if "clap-htsat" in str(model_name):
+            cfg.update(frequency_min=50.0, source="published preprocessor_config.json of laion/clap-htsat-* (frequency_min 50)")
+        path = os.path.join(str(model_name), "preprocessor_config.json") if os.path.isdir(str(model_name)) else None
+        if path is None:
+            try:
+                from transformers.utils import cached_file
+                path = cached_file(model_name, "preprocessor_config.json", local_files_only=True)
+            except Exception:
+                path = None
+        if path and os.path.exists(path):
+            with open(path) as f:
+                js = json.load(f)
+            for k in ("frequency_min", "frequency_max", "truncation", "padding"):
+                if k in js:
+                    cfg[k] = js[k]
+            cfg["source"] = path
+        if given:
+            cfg.update(given)
+            cfg["source"] = "caller"
+        cfg["frequency_min"], cfg["frequency_max"] = float(cfg["frequency_min"]), float(cfg["frequency_max"])
+        return cfg
 
     @staticmethod
     def _load_pretrained(model_name: str) -> Dict[str, torch.Tensor]:
@@ -65,6 +102,7 @@ class CLAPAudioEncoder(nn.Module):
         sd = synthetic.random_state_dict(param_shapes(), seed, device)
         sd["audio_model.audio_encoder.batch_norm.running_mean"] = sd["audio_model.audio_encoder.batch_norm.running_mean"] * 40.0 - 12.0
         sd["audio_model.audio_encoder.batch_norm.running_var"] = sd["audio_model.audio_encoder.batch_norm.running_var"].abs() * 400.0 + 40.0
+        kw.setdefault("feature_config", {"frequency_min": 0.0, "frequency_max": 14000.0})   # the goldens' extractor (class defaults)
         return cls(device=device, state_dict=sd, dtype=dtype, **kw)
 
     def freeze_encoder(self):

@@ -366,3 +366,17 @@ class HierarchicalAudioV4(Native):
             hierarchy["tokens10"] = tokens10
             return tokens77, hierarchy
         return tokens77
+
+    def encode(self, clap_features: torch.Tensor, with_tokens77: bool = True) -> Dict[str, torch.Tensor]:
+        """Conditioning entry with the interface of ImprovedHierarchicalAudioEncoder.encode, so that a stage-1/2/3
+        checkpoint of THIS class (the only hierarchical model the reference's scripts save: train_stage2.py:183-189,
+        train_stage3.py:262-271) can drive the audio attention processors.  The rigid 5-3-2 groups go to the UNet
+        levels the reference names for them (models/hierarchical_audio_v4.py:311-313, :319-321): ambience -> early
+        blocks, background -> mid blocks, foreground -> late blocks."""
+        tokens10, hierarchy = self.decomposer(clap_features, return_hierarchy=True)
+        out = {"tokens_10": tokens10,
+               "routed": {"early": hierarchy["ambience"].contiguous(), "mid": hierarchy["background"].contiguous(),
+                          "late": hierarchy["foreground"].contiguous()}}
+        if with_tokens77:
+            out["tokens_77"] = self.projector(tokens10)
+        return out

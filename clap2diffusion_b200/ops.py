@@ -233,10 +233,12 @@ _gn_ws = {}
 
 
 def _gn_workspace(device, n_doubles: int) -> torch.Tensor:
-    ws = _gn_ws.get(device)
+    """fp32-mode GroupNorm statistics scratch, one per (device, stream) so that concurrent streams never share it."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _gn_ws.get(key)
     if ws is None or ws.numel() < n_doubles:
         ws = torch.empty(max(n_doubles, 8192), device=device, dtype=torch.float64)
-        _gn_ws[device] = ws
+        _gn_ws[key] = ws
     return ws
 
 

@@ -108,12 +108,27 @@ class VAEDecoder:
         so = self._stats(B, cout, hw)
         return ops.conv3x3(h, w[f"{p}.conv2.weight"], w[f"{p}.conv2.bias"], residual=sc, impl=self.impl, stats=so), so
 
+    # The published SD-1.5 VAE files carry the attention block under its pre-0.19 diffusers names (query / key / value /
+    # proj_attn, 1x1-conv or linear shaped); diffusers renames them on load (_convert_deprecated_attention_blocks).
+    _ATTN_ALIASES = {"to_q": ("to_q", "query"), "to_k": ("to_k", "key"), "to_v": ("to_v", "value"),
+                     "to_out.0": ("to_out.0", "proj_attn")}
+
+    def _attn_param(self, a, name, kind):
+        for alias in self._ATTN_ALIASES[name]:
+            if f"{a}.{alias}.{kind}" in self._sd:
+                t = self._dev32(f"{a}.{alias}.{kind}")
+                return t.reshape(t.shape[0], -1) if kind == "weight" else t
+        have = sorted(k for k in self._sd if k.startswith(a + "."))
+        raise KeyError(f"VAE attention block {a!r}: no {kind} for {' / '.join(self._ATTN_ALIASES[name])} in the state dict "
+                       f"(keys under the block: {have})")
+
     def _pack_attention(self, a):
         self._norm(f"{a}.group_norm")
-        wq, wk, wv = (self._dev32(f"{a}.{n}.weight") for n in ("to_q", "to_k", "to_v"))
+        wq, wk, wv = (self._attn_param(a, n, "weight") for n in ("to_q", "to_k", "to_v"))
         self.w[f"{a}.qkv.weight"] = self._cast(torch.cat([wq, wk, wv], 0))
-        self.w[f"{a}.qkv.bias"] = torch.cat([self._dev32(f"{a}.{n}.bias") for n in ("to_q", "to_k", "to_v")], 0).contiguous()
-        self._lin(f"{a}.to_out.0")
+        self.w[f"{a}.qkv.bias"] = torch.cat([self._attn_param(a, n, "bias") for n in ("to_q", "to_k", "to_v")], 0).contiguous()
+        self.w[f"{a}.to_out.0.weight"] = self._cast(self._attn_param(a, "to_out.0", "weight"))
+        self.w[f"{a}.to_out.0.bias"] = self._attn_param(a, "to_out.0", "bias")
 
     def _mid_attention(self, x, xs, a="decoder.mid_block.attentions.0"):
         w = self.w

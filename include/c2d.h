@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 3   /* 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
+#define C2D_ABI_VERSION 4   /* 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
+                             *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
 enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
 enum { C2D_F32 = 0, C2D_BF16 = 1 };
@@ -38,8 +39,21 @@ enum { C2D_AUDIO_NONE = 0, C2D_AUDIO_ADD = 1, C2D_AUDIO_CONCAT = 2 };
 
 int c2d_abi_version(void);
 const char* c2d_last_error(void);
-/* Per-process, per-device one-time setup (driver entry points, max dynamic smem attributes). */
+/* Per-device one-time setup (checks the device is sm_100, resolves the tensor-map driver entry point).  Does NOT
+ * change the calling thread's current device and allocates NO device memory: the library's only state is a small
+ * per-device context ("caller owns every buffer incl. workspace ... c2d_init / c2d_destroy"). */
 int c2d_init(int device);
+/* Forgets the per-device context (the registered workspace pointer and cached device facts).  Nothing to free: the
+ * workspace belongs to the caller, tensor maps are built per launch and passed by value. */
+int c2d_destroy(int device);
+/* Split-K workspace of the small-plane 3x3 convolutions (fp32 partial slices; see c2d_conv3x3_ex).  The CALLER
+ * allocates `c2d_splitk_workspace_bytes()` bytes (256-byte aligned) of device memory and registers them; without a
+ * workspace those convolutions run un-split (same results, lower occupancy at 8x8 latents).  One workspace per
+ * device: launches that may use it concurrently on DIFFERENT streams of one device need the caller to give each
+ * stream its own (call c2d_set_workspace before enqueueing on the other stream) -- everything else in the library
+ * is re-entrant across streams.  workspace = NULL removes it. */
+long long c2d_splitk_workspace_bytes(void);
+int c2d_set_workspace(int device, void* workspace, long long bytes);
 /* Number of kernels this library has launched since load (claim for bench.py's gpu_launches). */
 unsigned long long c2d_launch_count(void);
 /* Name of the kernel family the calling thread launched last (e.g. "conv3x3_tc", "linear_simt"): lets

@@ -210,6 +210,38 @@ def audio_goldens():
     print("audio goldens written to", GOLD)
 
 
+def mask_goldens():
+    """attention_mask pass-through (reference audio_attention_processor.py:129 -> attn.get_attention_scores): the
+    UNMODIFIED reference processor with a key-padding mask in the form diffusers prepares it ([B*heads, 1, T], additive
+    0 / -10000), 'add' mode, at the (256, 1280) site.  Sample 0 keeps 60 keys, sample 1 keeps 77."""
+    from oracle import audio as A
+    from oracle.pipeline import np_randn
+    from oracle.weights import synth_state_dict
+    ad, hi, ap, dap = _load_ref()
+    N, C, heads = 256, 1280, 8
+    ehs = torch.from_numpy(np_randn("ehs", (2, 77, 768)))
+    audio = torch.from_numpy(np_randn("audio10", (2, 10, 768))) * 0.3
+    psd = synth_state_dict(A.attn_processor_spec(), SEED)
+    attn = dap.Attention(C, cross_attention_dim=768, heads=heads, dim_head=C // heads)
+    asd = synth_state_dict(A.attn_site_spec(C), SEED, prefix=f"site{C}.")
+    asd = {k.split(".", 1)[1]: v for k, v in asd.items()}
+    _load(attn, asd)
+    h = torch.from_numpy(np_randn(f"h_{N}_{C}", (2, N, C)))
+    keep = torch.ones(2, 77, dtype=torch.bool)
+    keep[0, 60:] = False
+    bias = torch.zeros(2, 77).masked_fill(~keep, -10000.0)
+    mask = bias[:, None, None, :].expand(2, heads, 1, 77).reshape(2 * heads, 1, 77).contiguous()
+    proc = ap.AudioAttnProcessor(level="mid", mode="add")
+    _load(proc, psd)
+    with torch.no_grad():
+        ref = proc(attn, h, encoder_hidden_states=ehs, attention_mask=mask, audio={"mid": audio})
+        ref_nomask = proc(attn, h, encoder_hidden_states=ehs, audio={"mid": audio})
+    assert float((ref[0] - ref_nomask[0]).abs().max()) > 1e-3 and torch.equal(ref[1], ref_nomask[1])
+    rows = np.arange(0, N, 4)
+    np.savez_compressed(os.path.join(GOLD, "attn_processor_mask.npz"), seed=SEED, keep=keep.numpy(), rows=rows, out=ref.numpy()[:, rows])
+    print("mask golden written")
+
+
 def unet_goldens():
     """Oracle-generated (UNPINNED) UNet / pipeline vectors for the CUDA parity tests."""
     import time
@@ -282,10 +314,14 @@ if __name__ == "__main__":
     ap_.add_argument("--unet", action="store_true")
     ap_.add_argument("--only-unet", action="store_true")
     ap_.add_argument("--only-full", action="store_true", help="only the 50-step config-2 / config-3 trajectories")
+    ap_.add_argument("--only-mask", action="store_true", help="only the attention_mask golden of the processor")
     a = ap_.parse_args()
     sys.path.insert(0, ROOT)
     if a.only_full:
         full_trajectory_goldens()
+        sys.exit(0)
+    if a.only_mask:
+        mask_goldens()
         sys.exit(0)
     if not a.only_unet:
         audio_goldens()

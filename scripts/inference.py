@@ -7,10 +7,21 @@ runs the real denoising loop on libc2d kernels instead of fabricating a random i
 (reference :153-166): CLAP embedding -> hierarchical audio tokens -> audio attention processors on the
 SD-1.5 UNet -> 50 x (UNet + CFG + DDIM) -> VAE decode.
 
-No checkpoints, tokenizer files or pretrained CLAP exist on the box (no network): missing weights are
-random-initialised, the text states are the synthetic stand-in of ``clap2diffusion_b200.synthetic`` and the
-CLAP embedding is a deterministic stand-in derived from the waveform (the reference itself uses
-``torch.randn(1, 512)``, :85-90).  ``--audio synthetic:<seed>`` generates the 10 s / 48 kHz test clip.
+Checkpoints (same file names and dict keys as the reference's scripts write / read):
+  audio_projector_stage3_finetuned.pth | audio_projector_stage2.pth   {'hierarchical_state_dict': HierarchicalAudioV4,
+        'adapter_state_dict': AudioAdapter, ...}          (train_stage3.py:262-271, train_stage2.py:183-189)
+  hierarchical_v4_final.pth                               raw HierarchicalAudioV4 state dict (inference.py:53-59)
+  unet_adapter_final.pth                                  {'processor_early' | 'processor_mid' | 'processor_late':
+        AudioAttnProcessor state dicts[, 'hierarchical_state_dict': ImprovedHierarchicalAudioEncoder, 'mode']} -- the
+        reference names the file (inference.py:62-65) but never writes it; this is the layout this package saves.
+  unet.pth / vae_decoder.pth (diffusers key layout), clap_audio.pth (HF key layout).
+The audio conditioning of the image is switched ON only when trained audio weights were found for BOTH the
+hierarchical model and the attention processors: random-init processors (alpha = 0 -> gate 0.5) would add noise to
+the text states at all 16 attn2 sites.  Otherwise the run is text-only and says so loudly.
+
+No tokenizer / CLIP text encoder exists on the box (no network): ``--text`` is either a file with precomputed CLIP
+text states ([77,768] or [1,77,768]; .npy / .pt) or a prompt string, which is hashed into the synthetic stand-in of
+``clap2diffusion_b200.synthetic`` (with a warning).  ``--audio synthetic:<seed>`` generates the 10 s / 48 kHz test clip.
 """
 from __future__ import annotations
 
@@ -53,30 +64,80 @@ class AudioToImageInference:
         return torch.load(path, map_location="cpu", weights_only=True)
 
     def load_models(self):
-        """Loads whatever checkpoints exist (same file names and dict keys as the reference, :34-71) and
-        random-initialises the rest."""
-        ck = self._load("audio_projector_stage2.pth")
-        if ck is not None:
-            self.audio_adapter = AudioAdapter().to(self.device).eval()
-            if "adapter_state_dict" in ck:
+        """Loads whatever checkpoints exist (reference file names and dict keys, :34-71) and random-initialises the
+        rest.  Sets ``self.audio_conditioning`` (see the module docstring)."""
+        hier_sd, hier_src = None, None
+        for name in ("audio_projector_stage3_finetuned.pth", "audio_projector_stage2.pth"):
+            ck = self._load(name)
+            if ck is None:
+                continue
+            if "adapter_state_dict" in ck and not hasattr(self, "audio_adapter"):
+                self.audio_adapter = AudioAdapter().to(self.device).eval()
                 self.audio_adapter.load_state_dict(ck["adapter_state_dict"])
+            if "hierarchical_state_dict" in ck and hier_sd is None:
+                hier_sd, hier_src = ck["hierarchical_state_dict"], name
         ck = self._load("hierarchical_v4_final.pth")
-        if ck is not None:
+        if ck is not None and hier_sd is None:
+            hier_sd, hier_src = ck, "hierarchical_v4_final.pth"
+        if hier_sd is not None:
             self.hierarchical_model = HierarchicalAudioV4().to(self.device).eval()
-            self.hierarchical_model.load_state_dict(ck)
+            self.hierarchical_model.load_state_dict(hier_sd)
         unet_sd, vae_sd = self._load("unet.pth"), self._load("vae_decoder.pth")
+        ck = self._load("unet_adapter_final.pth")
+        mode = (ck or {}).get("mode", "add")
         if unet_sd is None or vae_sd is None:
             print("No SD-1.5 UNet / VAE checkpoint found: using random-init weights (synthetic run)")
-            self.pipeline = AudioToImagePipeline.random_init(seed=0, device=self.device, dtype=self.dtype)
+            self.pipeline = AudioToImagePipeline.random_init(seed=0, device=self.device, dtype=self.dtype, mode=mode)
         else:
-            self.pipeline = AudioToImagePipeline(unet_sd, vae_sd, device=self.device, dtype=self.dtype)
-        ck = self._load("unet_adapter_final.pth")
+            self.pipeline = AudioToImagePipeline(unet_sd, vae_sd, device=self.device, dtype=self.dtype, mode=mode)
+        have_hier = have_proc = False
         if ck is not None:
-            if "hierarchical_state_dict" in ck:
+            if "hierarchical_state_dict" in ck:          # ImprovedHierarchicalAudioEncoder (soft decomposition + router)
                 self.pipeline.hier.load_state_dict({k: v.to(self.device) for k, v in ck["hierarchical_state_dict"].items()})
-            for lvl, names in self.pipeline.manager.level_mapping.items():
-                if names and f"processor_{lvl}" in ck:
+                have_hier, hier_src = True, "unet_adapter_final.pth"
+            levels = [lvl for lvl, names in self.pipeline.manager.level_mapping.items() if names]
+            for lvl in levels:
+                if f"processor_{lvl}" in ck:
+                    names = self.pipeline.manager.level_mapping[lvl]
                     self.pipeline.unet.sites[names[0][:-len(".processor")]].processor.load_state_dict(ck[f"processor_{lvl}"])
+            have_proc = all(f"processor_{lvl}" in ck for lvl in levels)
+        if not have_hier and hasattr(self, "hierarchical_model"):
+            # the reference's own checkpoints hold the legacy 5-3-2 model: it drives the processors through its
+            # encode() (ambience -> early, background -> mid, foreground -> late)
+            self.pipeline.sampler.hier = self.hierarchical_model
+            have_hier = True
+        self.audio_conditioning = have_hier and have_proc
+        if self.audio_conditioning:
+            print(f"Audio conditioning ON: hierarchical model from {hier_src}, attention processors from unet_adapter_final.pth")
+        else:
+            missing = [n for n, ok in (("hierarchical model", have_hier), ("attention processors (unet_adapter_final.pth)", have_proc)) if not ok]
+            print("=" * 60 + f"\nWARNING: no trained weights for the {' and the '.join(missing)}: audio conditioning is OFF\n"
+                  "         (text-only image; random-init processors would corrupt the text states).\n" + "=" * 60)
+
+    def save_unet_adapter(self, path=None):
+        """Writes ``unet_adapter_final.pth`` (the layout load_models reads): one state dict per processor level."""
+        path = Path(path) if path is not None else self.checkpoint_dir / "unet_adapter_final.pth"
+        ck = {"mode": "add"}
+        for lvl, names in self.pipeline.manager.level_mapping.items():
+            if names:
+                proc = self.pipeline.unet.sites[names[0][:-len(".processor")]].processor
+                ck["mode"] = proc.mode
+                ck[f"processor_{lvl}"] = {k: v.detach().cpu() for k, v in proc.state_dict().items()}
+        torch.save(ck, path)
+        return path
+
+    def text_states(self, text_prompt):
+        """[1,77,768] text states: a .npy / .pt file of precomputed CLIP states, else the synthetic stand-in."""
+        sp = str(text_prompt)
+        if sp.endswith((".npy", ".pt")) and os.path.exists(sp):
+            a = np.load(sp) if sp.endswith(".npy") else torch.load(sp, map_location="cpu", weights_only=True).float().numpy()
+            a = np.asarray(a, dtype=np.float32).reshape(-1, 77, 768)[:1]
+            return torch.from_numpy(a).to(self.device, self.dtype)
+        if sp and not getattr(self, "_warned_text", False):
+            print("  (no CLIP text encoder on this box: the prompt is hashed into synthetic text states; pass a .npy / .pt "
+                  "file of [77,768] CLIP states for real conditioning)")
+            self._warned_text = True
+        return torch.from_numpy(synthetic.text_states(sp)[None]).to(self.device, self.dtype)
 
     # ------------------------------------------------------------------ audio
     def load_audio(self, audio_path, duration=10):
@@ -145,10 +206,12 @@ class AudioToImageInference:
         print(f"  CFG Scale: {guidance_scale}")
         noise_seed = seed if seed is not None else int(np.random.randint(0, 2 ** 31 - 1))
         out = self.pipeline.sampler.sample(
-            clap, torch.from_numpy(synthetic.text_states(text_prompt)[None]).to(self.device, self.dtype),
+            clap, self.text_states(text_prompt),
             torch.from_numpy(synthetic.text_states("")[None]).to(self.device, self.dtype),
             torch.from_numpy(synthetic.init_noise(noise_seed)[None]).to(self.device),
-            steps=num_inference_steps, guidance=guidance_scale, use_audio=use_hierarchical, decode=True)
+            steps=num_inference_steps, guidance=guidance_scale,
+            use_audio=bool(use_hierarchical and self.audio_conditioning), decode=True)
+        self.last_latents = out["latents"]
         img = out["image"][0].cpu().numpy().transpose(1, 2, 0)             # [-1,1] NCHW -> HWC uint8 on the host
         return Image.fromarray(((np.clip(img, -1.0, 1.0) + 1.0) * 127.5).astype(np.uint8))
 

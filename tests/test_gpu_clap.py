@@ -107,7 +107,8 @@ def test_drop_in_audio_encoder(clap_setup):
     """models.audio_encoder.CLAPAudioEncoder: reference call surface (list of numpy clips / tensors, preprocess_audio)."""
     from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder, compute_audio_text_similarity
     g, sd, waves = clap_setup
-    enc = CLAPAudioEncoder(device=DEV, state_dict=sd, dtype=torch.float32)
+    # the goldens come from a ClapFeatureExtractor with the class defaults (frequency_min 0)
+    enc = CLAPAudioEncoder(device=DEV, state_dict=sd, dtype=torch.float32, feature_config={"frequency_min": 0.0})
     clips = [w for w in waves.cpu().numpy()]
     emb = enc.encode_audio(clips, 48000)                      # list of clips
     assert tuple(emb.shape) == (2, 512) and rel(emb, torch.from_numpy(g["embedding"])) < 1e-4
@@ -121,3 +122,20 @@ def test_drop_in_audio_encoder(clap_setup):
     rnd_enc = CLAPAudioEncoder.random_init(seed=3, device=DEV)
     z = rnd_enc.encode_audio(waves)
     assert torch.isfinite(z).all() and abs(float(z.norm(dim=-1).mean()) - 1.0) < 1e-4
+
+
+def test_feature_extractor_config_frequency_min(clap_setup):
+    """laion/clap-htsat-unfused publishes frequency_min = 50 in preprocessor_config.json (the reference reads it through
+    ClapProcessor.from_pretrained, models/audio_encoder.py:47): the drop-in defaults to it for that checkpoint family and
+    its GPU log-mel then equals Hugging Face's ClapFeatureExtractor(frequency_min=50) run here."""
+    from transformers import ClapFeatureExtractor
+    from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder
+    g, sd, waves = clap_setup
+    enc = CLAPAudioEncoder(device=DEV, state_dict=sd, dtype=torch.float32)
+    assert enc.feature_config["frequency_min"] == 50.0 and enc.tower.frequency_min == 50.0
+    fe = ClapFeatureExtractor(truncation="rand_trunc", padding="repeatpad", frequency_min=50, frequency_max=14000)
+    ref = fe([w for w in waves.cpu().numpy()], sampling_rate=48000, return_tensors="pt")["input_features"]   # [B,1,1001,64]
+    unbn = lambda t: (t.log_mel(waves) - t.w["bn_b"]) / t.w["bn_a"]          # undo the folded eval-mode BatchNorm
+    assert rel(unbn(enc.tower).reshape(ref.shape), ref) < 5e-5
+    enc0 = CLAPAudioEncoder(device=DEV, state_dict=sd, dtype=torch.float32, feature_config={"frequency_min": 0.0})
+    assert rel(unbn(enc0.tower).reshape(ref.shape), ref) > 1e-3              # the setting matters

@@ -105,6 +105,50 @@ def test_attn_processor_sites(gold, N, C, dtype, tol):
         assert rel_l2(out_na[:, rows].float(), _t(g[f"out_noaudio_{N}_{C}"])) < tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_attn_processor_attention_mask_and_kv_cache(gold, dtype, tol):
+    """attention_mask pass-through (reference :129) against the UNMODIFIED reference processor's output (additive
+    [B*heads,1,T] key-padding mask as diffusers prepares it), the boolean [B,T] form, loud refusal of general biases, and
+    the identity-keyed K/V cache of the stand-alone call (a denoising loop projects K/V once per image)."""
+    g = gold("attn_processor_mask.npz")
+    seed, N, C, heads = int(g["seed"]), 256, 1280, 8
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    ehs = _t(np_randn("ehs", (2, 77, 768))).to(DEV)
+    audio = (_t(np_randn("audio10", (2, 10, 768))) * 0.3).to(DEV)
+    asd = synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.")
+    site = _Site({k.split(".", 1)[1]: torch.from_numpy(v).to(DEV) for k, v in asd.items()})
+    h = _t(np_randn(f"h_{N}_{C}", (2, N, C))).to(DEV).to(dtype)
+    keep = _t(g["keep"]).to(DEV)
+    bias = torch.zeros(2, 77, device=DEV).masked_fill(~keep, -10000.0)
+    mask = bias[:, None, None, :].expand(2, heads, 1, 77).reshape(2 * heads, 1, 77).contiguous()
+    rows = torch.from_numpy(g["rows"]).to(DEV)
+    proc = pproc.AudioAttnProcessor(level="mid", mode="add")
+    proc.load_state_dict(psd)
+    proc = proc.to(DEV).eval()
+    with torch.no_grad():
+        out = proc(site, h, encoder_hidden_states=ehs, attention_mask=mask, audio={"mid": audio})
+        out_b = proc(site, h, encoder_hidden_states=ehs, attention_mask=keep, audio={"mid": audio})
+        assert rel_l2(out[:, rows].float(), _t(g["out"])) < tol
+        assert torch.equal(out, out_b)
+        with pytest.raises(Exception):          # a per-query bias is not a key-padding mask: refused, never ignored
+            proc(site, h, encoder_hidden_states=ehs, attention_mask=torch.randn(2 * heads, N, 77, device=DEV), audio={"mid": audio})
+        with pytest.raises(Exception):
+            proc(site, h, encoder_hidden_states=ehs, attention_mask=torch.zeros(2, 50, device=DEV), audio={"mid": audio})
+        # K/V cache: same ehs / audio tensors -> one projection for many "steps"; an in-place change is a miss
+        aud = {"mid": audio}
+        n0 = proc.kv_projections
+        o1 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        for _ in range(3):
+            o2 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 1 and torch.equal(o1, o2)
+        ehs.mul_(1.25)
+        o3 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 2 and not torch.equal(o1, o3)
+        proc.alpha.fill_(1.5)          # (no_grad) in-place parameter update bumps the version counter
+        proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 3
+
+
 def test_gated_xattn(gold):
     g = gold("gated_xattn.npz")
     m = _load(padapter.AudioCrossAttention(320), synth_state_dict(A.gated_xattn_spec(320), int(g["seed"])))

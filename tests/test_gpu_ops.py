@@ -212,6 +212,27 @@ def test_conv3x3_ex_stats(B, H, Cin, Cout, stride):
     _stats_close(stats, y, B, Cout)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 96, 64, 320, 320, 1), (1, 48, 32, 640, 640, 1), (2, 24, 16, 1280, 1280, 1),
+                                                   (2, 12, 8, 1280, 1280, 1), (2, 96, 64, 320, 320, 2), (1, 6, 4, 640, 640, 1),
+                                                   # output widths the tcgen05 tiler does not take -> FFMA kernel + stand-alone statistics
+                                                   (2, 64, 96, 320, 320, 1), (1, 12, 24, 640, 320, 1), (2, 64, 96, 320, 320, 2), (1, 16, 16, 20, 32, 1)])
+def test_conv3x3_non_square_planes(B, H, W, Cin, Cout, stride):
+    """Latents of non-square images (e.g. 768 x 512 -> 96 x 64): heights that are not powers of two run on the tcgen05
+    tiler, widths it cannot box fall back to the FFMA kernel inside c2d_conv3x3_ex -- both with channel statistics."""
+    x = rnd(B, H, W, Cin, dtype=BF16)
+    w = ops.pack_conv3x3(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1), BF16)
+    b, rv = rnd(Cout, seed=2), rnd(B, Cout, seed=4)
+    Ho, Wo = H // stride, W // stride
+    r = rnd(B, Ho, Wo, Cout, dtype=BF16, seed=3)
+    stats = torch.zeros(B * Cout * 2, device=DEV, dtype=torch.int64)
+    y = ops.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride, stats=stats)
+    assert tuple(y.shape) == (B, Ho, Wo, Cout)
+    assert rel(y, T.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride)) < 1e-2
+    assert rel(y, ops.conv3x3(x, w, b, rowvec=rv, residual=r, stride=stride, impl=ops.IMPL_SIMT)) < 1e-2
+    if Cout % 8 == 0:
+        _stats_close(stats, y, B, Cout)
+
+
 @pytest.mark.parametrize("B,HW,C1,C2", [(2, 4096, 320, 0), (2, 64, 1280, 1280), (3, 256, 1280, 640), (1, 1024, 640, 320),
                                         (16, 1024, 640, 0), (2, 4096, 640, 320), (1, 16384, 128, 0)])
 def test_group_norm_apply_from_channel_stats(B, HW, C1, C2):

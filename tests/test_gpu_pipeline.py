@@ -21,6 +21,10 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
+def to_torch_(sd):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+
+
 @pytest.fixture(scope="module")
 def W():
     return PL.build_weights(seed=0, with_vae=True)
@@ -58,6 +62,25 @@ def test_unet_forward_16x16(gold, W, pipe32, pipe16):
         assert rel_l2(taps["conv_in"].float().permute(0, 3, 1, 2), _t(g["conv_in"])) < tol
         assert rel_l2(taps["mid"].float().permute(0, 3, 1, 2), _t(g["mid"])) < tol
         assert rel_l2(eps, _t(g["eps"])) < tol, pipe.dtype
+
+
+@pytest.mark.parametrize("h,w", [(24, 16), (16, 24)])
+def test_unet_forward_non_square_latent(W, pipe32, pipe16, h, w):
+    """Non-square latents (a 768 x 512 image is 96 x 64; here the same 3:2 / 2:3 geometry at a size the CPU oracle
+    finishes quickly): the bf16 product path must take them (tcgen05 tiler or its in-library FFMA fallback) and agree
+    with the oracle and with the fp32 path."""
+    clap = _t(PL.clap_embedding(0))[None]
+    x = _t(PL.np_randn("nsq", (1, 4, h, w)))
+    ctx = _t(PL.text_states("a beach"))[None]
+    with torch.no_grad():
+        hier = A.improved_hier_forward(W["hier"], clap)
+        ref = sd15.unet_forward(W["unet"], x, 321.0, ctx, PL.make_attn2_hook(W, hier["routed"], "add"))
+    for pipe, tol in ((pipe32, 1e-4), (pipe16, 3e-2)):
+        with torch.no_grad():
+            routed = pipe.hier.encode(clap.to(DEV), with_tokens77=False)["routed"]
+            eps = pipe.unet(x.to(DEV), 321.0, ctx.to(DEV), cross_attention_kwargs={"audio": routed})
+        assert tuple(eps.shape) == (1, 4, h, w)
+        assert rel_l2(eps, ref) < tol, (pipe.dtype, h, w)
 
 
 def test_config1_fp32_per_step_latents_and_psnr(gold, pipe32):
@@ -173,6 +196,65 @@ def test_inference_cli_end_to_end(tmp_path):
     assert im.size == (512, 512) and im.mode == "RGB"
     a = np.asarray(im).astype(np.float32)
     assert a.std() > 1.0            # not a constant image
+
+
+def _load_cli():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("c2d_inference", os.path.join(os.path.dirname(__file__), "..", "scripts", "inference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_checkpoint_round_trip_through_cli(tmp_path, W, capsys):
+    """checkpoints in the REFERENCE's layout -- `audio_projector_stage2.pth` = {'step',
+    'hierarchical_state_dict' (HierarchicalAudioV4), 'adapter_state_dict' (AudioAdapter), 'optimizer_state_dict', 'config'}
+    (train_stage2.py:183-189), `hierarchical_v4_final.pth` = raw state dict (inference.py:53-59), `unet_adapter_final.pth`
+    (processor state dicts) -- are written, loaded through the drop-in CLI class, and REACH the image: the loaded
+    modules equal the written tensors, audio conditioning switches on, and the latents equal a direct sampler run wired
+    with the same weights (and differ from the text-only run).  Without processor weights the CLI stays text-only."""
+    from oracle.weights import synth_state_dict
+    from clap2diffusion_b200.models.audio_adapter_v4 import AudioAdapter
+    from clap2diffusion_b200.models.hierarchical_audio_v4 import HierarchicalAudioV4
+    mod = _load_cli()
+    legacy_sd = to_torch_(synth_state_dict(A.legacy_hier_spec(), 21))
+    assert set(legacy_sd) == set(HierarchicalAudioV4().state_dict())          # the reference's keys (App. D contract)
+    assert set(W["adapter"]) == set(AudioAdapter().state_dict())
+    torch.save({"step": 7, "hierarchical_state_dict": legacy_sd, "adapter_state_dict": W["adapter"],
+                "optimizer_state_dict": {"state": {}, "param_groups": []}, "config": {"learning_rate": 1e-4}},
+               tmp_path / "audio_projector_stage2.pth")
+    # (1) hierarchical model only: conditioning must stay OFF (random processors would corrupt the text states)
+    inf = mod.AudioToImageInference(checkpoint_dir=str(tmp_path))
+    assert not inf.audio_conditioning and "audio conditioning is OFF" in capsys.readouterr().out
+    for k, v in inf.hierarchical_model.state_dict().items():
+        assert torch.equal(v.cpu(), legacy_sd[k]), k
+    for k, v in inf.audio_adapter.state_dict().items():
+        assert torch.equal(v.cpu(), W["adapter"][k]), k
+    inf.generate("synthetic:3", "a beach", num_inference_steps=3, seed=1)
+    lat_text_only = inf.last_latents.clone()
+    # (2) + processor weights (written by the package's own saver after loading trained values) -> ON
+    for lvl, names in inf.pipeline.manager.level_mapping.items():
+        inf.pipeline.unet.sites[names[0][:-len(".processor")]].processor.load_state_dict(W[f"proc_{lvl}"])
+    inf.save_unet_adapter()
+    torch.save(legacy_sd, tmp_path / "hierarchical_v4_final.pth")
+    inf2 = mod.AudioToImageInference(checkpoint_dir=str(tmp_path))
+    assert inf2.audio_conditioning and "Audio conditioning ON" in capsys.readouterr().out
+    for lvl, names in inf2.pipeline.manager.level_mapping.items():
+        psd = inf2.pipeline.unet.sites[names[0][:-len(".processor")]].processor.state_dict()
+        for k, v in psd.items():
+            assert torch.equal(v.cpu(), W[f"proc_{lvl}"][k]), (lvl, k)
+    inf2.generate("synthetic:3", "a beach", num_inference_steps=3, seed=1)
+    lat_audio = inf2.last_latents.clone()
+    assert rel_l2(lat_audio, lat_text_only) > 1e-3                          # the trained audio weights reach the image
+    inf2.generate("synthetic:3", "a beach", num_inference_steps=3, seed=1, use_hierarchical=False)
+    assert torch.equal(inf2.last_latents, lat_text_only)                     # --no_hierarchical == text-only
+    # the legacy model routes ambience -> early, background -> mid, foreground -> late (reference :311-313)
+    clap = inf2.extract_clap_embedding(inf2.load_audio("synthetic:3"))
+    enc = inf2.hierarchical_model.encode(clap, with_tokens77=False)
+    _, hz = inf2.hierarchical_model(clap, return_intermediate=True)
+    assert torch.equal(enc["routed"]["early"], hz["ambience"]) and torch.equal(enc["routed"]["late"], hz["foreground"])
+    assert tuple(enc["routed"]["mid"].shape) == (1, 3, 768)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])

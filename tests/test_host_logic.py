@@ -153,6 +153,46 @@ def test_attn_processor_module(gold):
             assert rel_l2(o4.reshape(2, C, 64).transpose(1, 2)[:, rows], _t(g[f"out_add_{N}_{C}"])) < 5e-6
 
 
+def test_attn_processor_mask_and_kv_cache_host_logic(gold):
+    """attention_mask reduction (additive [B*heads,1,T] / boolean [B,T] key-padding masks; general biases refused) against
+    the unmodified reference's output, and the identity-keyed K/V cache of the stand-alone call."""
+    g = gold("attn_processor_mask.npz")
+    seed, N, C, heads = int(g["seed"]), 256, 1280, 8
+    psd = to_torch(synth_state_dict(A.attn_processor_spec(), seed))
+    ehs = _t(np_randn("ehs", (2, 77, 768)))
+    audio = _t(np_randn("audio10", (2, 10, 768))) * 0.3
+    asd = synth_state_dict(A.attn_site_spec(C), seed, prefix=f"site{C}.")
+    site = _Site(to_torch({k.split(".", 1)[1]: v for k, v in asd.items()}))
+    h = _t(np_randn(f"h_{N}_{C}", (2, N, C)))
+    keep = _t(g["keep"])
+    bias = torch.zeros(2, 77).masked_fill(~keep, -10000.0)
+    mask = bias[:, None, None, :].expand(2, heads, 1, 77).reshape(2 * heads, 1, 77).contiguous()
+    proc = pproc.AudioAttnProcessor(level="mid", mode="add").eval()
+    proc.load_state_dict(psd)
+    aud = {"mid": audio}
+    with torch_ops.installed(), torch.no_grad():
+        out = proc(site, h, encoder_hidden_states=ehs, attention_mask=mask, audio=aud)
+        out_b = proc(site, h, encoder_hidden_states=ehs, attention_mask=keep, audio=aud)
+        assert rel_l2(out[:, g["rows"]], _t(g["out"])) < 5e-6
+        assert torch.equal(out, out_b)
+        for bad in (torch.randn(2 * heads, N, 77), torch.zeros(2, 50), bias[:, None, :] * 0.5 - 1.0,
+                    torch.full((2, 77), -10000.0)):
+            with pytest.raises(Exception):
+                proc(site, h, encoder_hidden_states=ehs, attention_mask=bad, audio=aud)
+        n0 = proc.kv_projections
+        o1 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        o2 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 1 and torch.equal(o1, o2)
+        ehs.mul_(1.25)                                   # in-place change of the text states: version bump -> miss
+        o3 = proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 2 and not torch.equal(o1, o3)
+        proc.alpha.fill_(1.5)                            # parameter update -> miss
+        proc(site, h, encoder_hidden_states=ehs, audio=aud)
+        assert proc.kv_projections == n0 + 3
+        proc(site, h, encoder_hidden_states=ehs, audio={"mid": audio.clone()})      # another audio tensor -> miss
+        assert proc.kv_projections == n0 + 4
+
+
 def test_attn_processor_decoupled_mode():
     """Design extension (no reference counterpart): text and audio branches with separate softmaxes, audio branch
     scaled by sigmoid(alpha) and added -- host logic vs the oracle's definition."""
@@ -301,6 +341,29 @@ def test_vae_host_logic_vs_oracle(W):
     assert rel_l2(img, ref) < 2e-5
 
 
+def test_vae_legacy_attention_key_names(W):
+    """The published SD-1.5 VAE files use the pre-0.19 diffusers attention names (query / key / value / proj_attn, stored
+    as 1x1 convolutions): accepted as aliases; a state dict with neither raises a KeyError that lists the block's keys."""
+    from clap2diffusion_b200.vae import VAEDecoder
+    a = "decoder.mid_block.attentions.0"
+    legacy = {}
+    for k, v in W["vae"].items():
+        for new, old in (("to_q", "query"), ("to_k", "key"), ("to_v", "value"), ("to_out.0", "proj_attn")):
+            if k.startswith(f"{a}.{new}."):
+                k = k.replace(f"{a}.{new}.", f"{a}.{old}.")
+                v = v[:, :, None, None] if k.endswith("weight") else v
+        legacy[k] = v
+    assert f"{a}.query.weight" in legacy and f"{a}.to_q.weight" not in legacy and legacy[f"{a}.proj_attn.weight"].dim() == 4
+    z = _t(PL.init_noise(3, 8, 8))[None] * 0.5
+    with torch_ops.installed(), torch.no_grad():
+        ref = VAEDecoder(W["vae"], device="cpu", dtype=torch.float32).decode(z)
+        img = VAEDecoder(legacy, device="cpu", dtype=torch.float32).decode(z)
+        assert torch.equal(img, ref)
+        broken = {k: v for k, v in legacy.items() if not k.startswith(f"{a}.key.")}
+        with pytest.raises(KeyError, match="to_k / key"):
+            VAEDecoder(broken, device="cpu", dtype=torch.float32)
+
+
 def test_vae_encoder_host_logic_vs_oracle():
     """AutoencoderKL encoder: product launch sequence (Downsample2D as conv3x3_down, folded latent
     scaling) == oracle restatement, and the state-dict contract (34,163,592 + 72 parameters)."""
@@ -362,3 +425,23 @@ def test_clap_tower_host_logic_vs_oracle(gold):
     assert rel_l2(taps["pooled"], _t(g["pooled"])) < 1e-4
     assert rel_l2(emb, _t(g["embedding"])) < 1e-4
     assert int(g["n_params"]) == 28190872
+
+
+def test_clap_mel_filter_bank_and_feature_config(tmp_path):
+    """Slaney filter bank for a configurable range against Hugging Face's audio_utils.mel_filter_bank, and the resolution
+    order of the feature-extractor settings: caller > preprocessor_config.json > published laion/clap-htsat-* > class defaults."""
+    import json
+    from transformers.audio_utils import mel_filter_bank
+    from clap2diffusion_b200 import clap as pclap
+    from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder
+    for fmin, fmax in ((0.0, 14000.0), (50.0, 14000.0), (20.0, 12000.0)):
+        ref = mel_filter_bank(num_frequency_bins=513, num_mel_filters=64, min_frequency=fmin, max_frequency=fmax,
+                              sampling_rate=48000, norm="slaney", mel_scale="slaney")
+        assert np.allclose(pclap._slaney_mel_filters(fmin, fmax), ref, rtol=1e-9, atol=1e-12), (fmin, fmax)
+    assert CLAPAudioEncoder._feature_config("laion/clap-htsat-unfused", None)["frequency_min"] == 50.0
+    assert CLAPAudioEncoder._feature_config("some/other-model", None)["frequency_min"] == 0.0
+    with open(tmp_path / "preprocessor_config.json", "w") as f:
+        json.dump({"frequency_min": 30, "frequency_max": 13000, "truncation": "rand_trunc", "padding": "repeatpad"}, f)
+    cfg = CLAPAudioEncoder._feature_config(str(tmp_path), None)
+    assert (cfg["frequency_min"], cfg["frequency_max"]) == (30.0, 13000.0) and cfg["source"].endswith("preprocessor_config.json")
+    assert CLAPAudioEncoder._feature_config(str(tmp_path), {"frequency_min": 10})["frequency_min"] == 10.0
