@@ -36,6 +36,4 @@ class Native(nn.Module):
 
 
 def require_cuda(x: torch.Tensor, who: str) -> None:
-    if not x.is_cuda and not ops.TEST_DOUBLE:
-        from .._lib import C2DError
-        raise C2DError(f"{who} runs on CUDA only (libc2d has no CPU path); got a {x.device} tensor")
+    ops.require_cuda(x, who)

@@ -232,8 +232,7 @@ class AudioAttnProcessor(nn.Module):
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
                  scale: float = 1.0, **cross_attention_kwargs) -> torch.Tensor:
-        if not hidden_states.is_cuda and not ops.TEST_DOUBLE:
-            raise C2DError("AudioAttnProcessor runs on CUDA only (libc2d has no CPU path)")
+        ops.require_cuda(hidden_states, "AudioAttnProcessor")
         if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "norm_cross", None):
             raise C2DError("spatial_norm / norm_cross attention variants are not on the SD-1.5 path")
         x = hidden_states

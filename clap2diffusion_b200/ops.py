@@ -16,9 +16,12 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = _lib.IMPL_AUTO, _lib.IMPL_SIMT, _lib.IMPL_T
 ACT_NONE, ACT_GELU, ACT_SILU, ACT_RELU = _lib.ACT_NONE, _lib.ACT_GELU, _lib.ACT_SILU, _lib.ACT_RELU
 AUDIO_ADD, AUDIO_CONCAT = _lib.AUDIO_ADD, _lib.AUDIO_CONCAT
 
-# Set ONLY by tests/torch_ops.py while it swaps these functions for torch doubles (host-logic tests on a
-# machine without a GPU).  The product never sets it; with it False every op demands CUDA tensors.
-TEST_DOUBLE = False
+
+def require_cuda(x, who: str) -> None:
+    """CUDA-only guard of the drop-in modules: the library has no CPU path and says so instead of falling back."""
+    if not x.is_cuda:
+        raise _lib.C2DError(f"{who} runs on CUDA only (libc2d has no CPU path); got a {x.device} tensor")
+
 
 # Per-op profiling for bench.py's roofline: when PROFILE is a list, every op appends
 # (kernel_name, flops, bytes, start_event, end_event) recorded on the launching stream.
@@ -353,8 +356,6 @@ class XattnKV:
 
 def xattn_supported(x, heads: int, T: int, T2: int = 0) -> bool:
     """True when the fused cross-attention kernel takes this site (bf16, SD-1.5 shapes); no device work."""
-    if TEST_DOUBLE:
-        return True
     if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 3:
         return False
     return bool(lib.c2d_xattn_supported(x.shape[-1], int(heads), x.shape[1], int(T), int(T2), _lib.BF16))
@@ -364,7 +365,7 @@ def xattn_packable(C: int, heads: int, T: int, dtype, T2: int = 0) -> bool:
     """True when c2d_xattn_pack_kv takes this site (bf16, head dims / key counts inside the fused kernel)."""
     if dtype != torch.bfloat16:
         return False
-    return True if TEST_DOUBLE else int(lib.c2d_xattn_packed_bytes(int(C), int(heads), int(T), int(T2))) > 0
+    return int(lib.c2d_xattn_packed_bytes(int(C), int(heads), int(T), int(T2))) > 0
 
 
 def xattn_pack_kv(kv, heads: int, kv2=None, lambda2: float = 1.0) -> XattnKV:

@@ -76,6 +76,27 @@ class AudioToImagePipeline:
             res["trace"] = [t.cpu().numpy() for t in out["trace"]]
         return res
 
+    @torch.no_grad()
+    def generate_from_waves(self, clap_encoder, waves: np.ndarray, ctx_cond: np.ndarray, ctx_uncond: np.ndarray,
+                            noise: np.ndarray, **kw) -> Dict[str, object]:
+        """The whole path of the north star from HOST waveforms: waves [B, 480000] fp32 (10 s @ 48 kHz) -> pinned H2D ->
+        GPU log-mel + HTSAT tower (models.audio_encoder.CLAPAudioEncoder) -> generate().  The CLAP embedding never
+        leaves the device."""
+        dev = self.device
+        w = torch.from_numpy(np.ascontiguousarray(waves, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+        clap = clap_encoder.encode_audio(w)
+
+        def h2d(a, dtype):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+            return t if dtype == torch.float32 else ops.cast(t, dtype)
+
+        out = self.sampler.sample(clap.float().contiguous(), h2d(ctx_cond, self.dtype), h2d(ctx_uncond, self.dtype),
+                                  h2d(noise, torch.float32), **kw)
+        res: Dict[str, object] = {"latents": out["latents"].cpu().numpy()}
+        if "image" in out:
+            res["image"] = out["image"].cpu().numpy()
+        return res
+
     @staticmethod
     def io_bytes(B: int, h: int = 64, w: int = 64, decode: bool = True):
         """(h2d, d2h) bytes per generate() call, counted from the tensors copied."""

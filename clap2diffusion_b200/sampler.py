@@ -87,7 +87,7 @@ class Sampler:
         for i in range(n_run):
             st["temb_row"].copy_(table[i])
             st["coef"].copy_(coefs[i])
-            if self.use_graph and not ops.TEST_DOUBLE:
+            if self.use_graph:
                 if st["graph"] is None:
                     st["graph"] = self._capture(st)
                 st["graph"].replay()

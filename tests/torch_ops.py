@@ -400,6 +400,11 @@ def l2_normalize(x, eps=1e-12, *, out=None):
     return F.normalize(x, dim=-1, eps=eps)
 
 
+def require_cuda(x, who):
+    """The CPU host-logic tests run the product's launch sequences on torch doubles: no device requirement."""
+    return None
+
+
 _NAMES = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and hasattr(real_ops, n)
           and n not in ("installed",)]
 
@@ -411,9 +416,7 @@ def installed():
     try:
         for n in _NAMES:
             setattr(real_ops, n, globals()[n])
-        real_ops.TEST_DOUBLE = True
         yield
     finally:
         for n, f in saved.items():
             setattr(real_ops, n, f)
-        real_ops.TEST_DOUBLE = False
