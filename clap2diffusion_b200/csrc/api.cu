@@ -45,7 +45,10 @@ int c2d_linear(const void* x, const void* w, const float* bias, const float* row
     C2D_REQUIRE(tc_ok, "linear: tcgen05 path needs bf16, K %% 8 == 0, ldx %% 8 == 0, aligned pointers");
     return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, nullptr, s);
   }
-  if (impl == C2D_IMPL_AUTO && tc_ok && M >= 64)
+  // tcgen05 from 64 rows up, and from 8 rows up when the layer is a weight-streaming one (>= 1 Mi weights: the audio
+  // projector / decomposer MLPs, 512 -> 24576 at batch 8..256) -- the tile's idle rows cost nothing there, the bf16
+  // weights are read exactly once; tiny layers with a handful of rows stay on the FFMA kernel (latency-bound either way)
+  if (impl == C2D_IMPL_AUTO && tc_ok && (M >= 64 || (M >= 8 && (long long)N * K >= (1ll << 20))))
     return linear_tc(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, false, nullptr, s);
   return linear_simt(x, w, bias, rowvec, rows_per_vec, residual, y, M, N, K, ldx, ldy, ldr, act, dtype, s);
 }

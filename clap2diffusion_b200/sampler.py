@@ -34,7 +34,10 @@ class Sampler:
         ctx2 = torch.cat([ctx_uncond, ctx_cond], dim=0).contiguous()
         kwargs = None
         if use_audio and self.hier is not None:
-            enc = self.hier.encode(clap.contiguous(), with_tokens77=False)
+            # the audio side runs in the UNet's compute dtype: bf16 -> its projector / decomposer GEMMs go to the
+            # tcgen05 kernel; the fp32 parity mode keeps everything on the FFMA kernels
+            a = clap.contiguous() if clap.dtype == self.unet.dtype else ops.cast(clap.contiguous(), self.unet.dtype)
+            enc = self.hier.encode(a, with_tokens77=False)
             routed2 = {k: torch.cat([v, v], dim=0).contiguous() for k, v in enc["routed"].items()}
             kwargs = {"audio": routed2}
         return self.unet.prepare_conditioning(ctx2, kwargs)

@@ -57,6 +57,49 @@ def test_improved_hier(gold):
     assert rel_l2(enc["assignments"], _t(g["assignments_T05"])) < 1e-5
 
 
+def _kernels(fn):
+    ops.PROFILE = []
+    out = fn()
+    torch.cuda.synchronize()
+    rec, ops.PROFILE = ops.PROFILE, None
+    names = {}
+    for r in rec:
+        names[r[0]] = names.get(r[0], 0) + 1
+    return out, names
+
+
+def test_audio_side_bf16_on_tensor_cores(gold):
+    """SURVEY 2.1 K8 / north star "projector MLPs": in bf16 the projector and decomposer GEMMs of
+    ImprovedHierarchicalAudioEncoder and AudioAdapter run on the tcgen05 kernel (weights streamed once as bf16) and stay
+    within 2e-2 of the goldens produced by the unmodified reference modules; at the benchmark batch (8) and at the
+    config-4 batch (256) a sample's tokens do not depend on its batch neighbours."""
+    g = gold("improved_hier.npz")
+    sd = synth_state_dict(A.improved_hier_spec(), int(g["seed"]))
+    for k, v in A.IMPROVED_BUFFERS.items():
+        sd[k] = np.asarray(v, dtype=np.float32)
+    m = _load(phier.ImprovedHierarchicalAudioEncoder(), sd)
+    clap = _t(g["clap"]).to(DEV)
+    rep = clap.repeat(86, 1)[:256].contiguous()
+    with torch.no_grad():
+        enc, ks = _kernels(lambda: m.encode(rep[:8].to(torch.bfloat16)))
+        enc256 = m.encode(rep.to(torch.bfloat16))
+    assert ks.get("linear_tc", 0) >= 20 and ks.get("attn_tc", 0) >= 4, ks      # the dense contractions are on tcgen05
+    for k in ("tokens_10", "assignments", "hierarchy_weights", "tokens_77"):
+        assert enc[k].shape[0] == 8 and rel_l2(enc[k][:3].float(), _t(g[k])) < 2e-2, k
+        assert rel_l2(enc256[k][:3].float(), _t(g[k])) < 2e-2, k
+    for lvl in ("early", "mid", "late"):
+        assert rel_l2(enc["routed"][lvl][:3].float(), _t(g[f"routed_{lvl}"])) < 2e-2
+        assert enc["routed"][lvl].dtype == torch.bfloat16
+    ga = gold("audio_adapter.npz")
+    ad = _load(padapter.AudioAdapter(), synth_state_dict(A.audio_adapter_spec(), int(ga["seed"])))
+    ca = _t(ga["clap"]).to(DEV).repeat(86, 1)[:256].contiguous()
+    with torch.no_grad():
+        out, ks = _kernels(lambda: ad(ca[:8].to(torch.bfloat16)))
+        out256 = ad(ca.to(torch.bfloat16))
+    assert ks.get("linear_tc", 0) >= 8, ks           # 512 -> 256 -> 24576 token generator, the four self-attention blocks
+    assert rel_l2(out[:3].float(), _t(ga["tokens"])) < 2e-2 and rel_l2(out256[:3].float(), _t(ga["tokens"])) < 2e-2
+
+
 def test_legacy_hier(gold):
     g = gold("legacy_hier.npz")
     m = _load(phier.HierarchicalAudioV4(), synth_state_dict(A.legacy_hier_spec(), int(g["seed"])))
