@@ -85,6 +85,20 @@ SIGNATURES = {
     "c2d_patch_merge": [_p, _p, _i, _i, _i, _i, _i, _p],
     "c2d_token_mean": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_l2_normalize": [_p, _p, _i, _i, _f, _p],
+    "c2d_group_norm_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _p],
+    "c2d_layer_norm_bwd": [_p, _p, _p, _p, _p, _i, _i, _f, _i, _p],
+    "c2d_geglu_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "c2d_attention_bwd": [_p] * 10 + [_i] * 5 + [_ll] * 16 + [_f, _i, _p],
+    "c2d_zero_insert2x": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_sumpool2x2": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_slice_channels": [_p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "c2d_mse_loss_grad": [_p, _p, _p, _p, _i, _i, _i, _f, _i, _p],
+    "c2d_colsum": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_gate_bwd": [_p, _p, _p, _p, _p, _i, _p],
+    "c2d_gelu_bwd_bcast": [_p, _p, _p, _i, _i, _i, _p],
+    "c2d_sumsq": [_p, _ll, _p, _p],
+    "c2d_clip_scale": [_p, _f, _p, _p, _p],
+    "c2d_adamw_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _p, _p],
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }

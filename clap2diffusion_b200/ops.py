@@ -767,3 +767,163 @@ def l2_normalize(x, eps: float = 1e-12, *, out=None):
         out = torch.empty_like(x)
     check(lib.c2d_l2_normalize(_f32(x, "x").data_ptr(), out.data_ptr(), B, D, float(eps), _stream()), "l2_normalize")
     return out
+
+
+# ======================================================================================================
+# Backward / optimiser entry points of the stage-3 fine-tune step (include/c2d.h "stage-3 fine-tune step")
+# ======================================================================================================
+def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None):
+    _dev(x)
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype
+    assert add is None or (add.is_contiguous() and add.shape == x.shape and add.dtype == x.dtype)
+    if out is None:
+        out = torch.empty_like(x)
+    with _Timed(0.0, 5 * _nb(x) + _nb(out)):
+        check(lib.c2d_group_norm_bwd(x.data_ptr(), dy.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), _ptr(add),
+                                     out.data_ptr(), B, HW, C, groups, float(eps), int(bool(silu)), _dt(x), _stream()), "group_norm_bwd")
+    return out
+
+
+def layer_norm_bwd(x, dy, gamma, eps=1e-5, *, add=None, out=None):
+    _dev(x)
+    C = x.shape[-1]
+    M = x.numel() // C
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype
+    assert add is None or (add.is_contiguous() and add.shape == x.shape and add.dtype == x.dtype)
+    if out is None:
+        out = torch.empty_like(x)
+    with _Timed(0.0, 4 * _nb(x) + _nb(out)):
+        check(lib.c2d_layer_norm_bwd(x.data_ptr(), dy.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(add), out.data_ptr(), M, C,
+                                     float(eps), _dt(x), _stream()), "layer_norm_bwd")
+    return out
+
+
+def geglu_bwd(ag, dy, *, out=None):
+    _dev(ag)
+    F = dy.shape[-1]
+    M = dy.numel() // F
+    assert ag.is_contiguous() and dy.is_contiguous() and ag.shape[-1] == 2 * F and ag.dtype == dy.dtype
+    if out is None:
+        out = torch.empty_like(ag)
+    with _Timed(0.0, _nb(ag, dy, out)):
+        check(lib.c2d_geglu_bwd(ag.data_ptr(), dy.data_ptr(), out.data_ptr(), M, F, _dt(ag), _stream()), "geglu_bwd")
+    return out
+
+
+def attention_bwd(q, k, v, o, dout, heads: int, dq, dk, dv, *, scale: Optional[float] = None):
+    """Adjoint of ops.attention.  q [B,Nq,h*d], k / v [B,Nkv,h*d], o / dout [B,Nq,h*d]; dq / dk / dv are caller-provided
+    (possibly strided) views with the same logical shapes as q / k / v."""
+    _dev(q)
+    B, Nq, C = q.shape
+    Nkv = k.shape[1]
+    d = C // heads
+    for t in (q, k, v, o, dout, dq, dk, dv):
+        assert t.stride(2) == 1 and t.dtype == q.dtype
+    if scale is None:
+        scale = d ** -0.5
+    ws = torch.empty(2, B, heads, Nq, device=q.device, dtype=torch.float32)
+    with _Timed(10.0 * B * heads * Nq * Nkv * d, _nb(q, k, v, o, dout, dq, dk, dv)):
+        check(lib.c2d_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), dq.data_ptr(),
+                                    dk.data_ptr(), dv.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), B, heads, Nq, Nkv, d,
+                                    q.stride(1), k.stride(1), v.stride(1), o.stride(1), dout.stride(1), dq.stride(1), dk.stride(1),
+                                    dv.stride(1), q.stride(0), k.stride(0), v.stride(0), o.stride(0), dout.stride(0), dq.stride(0),
+                                    dk.stride(0), dv.stride(0), float(scale), _dt(q), _stream()), "attention_bwd")
+    return dq, dk, dv
+
+
+def zero_insert2x(x):
+    _dev(x)
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    z = torch.empty(B, 2 * H, 2 * W, C, device=x.device, dtype=x.dtype)
+    with _Timed(0.0, _nb(x, z)):
+        check(lib.c2d_zero_insert2x(x.data_ptr(), z.data_ptr(), B, H, W, C, _dt(x), _stream()), "zero_insert2x")
+    return z
+
+
+def sumpool2x2(x):
+    _dev(x)
+    B, H2, W2, C = x.shape
+    assert x.is_contiguous() and H2 % 2 == 0 and W2 % 2 == 0
+    y = torch.empty(B, H2 // 2, W2 // 2, C, device=x.device, dtype=x.dtype)
+    with _Timed(0.0, _nb(x, y)):
+        check(lib.c2d_sumpool2x2(x.data_ptr(), y.data_ptr(), B, H2 // 2, W2 // 2, C, _dt(x), _stream()), "sumpool2x2")
+    return y
+
+
+def slice_channels(x, c0: int, cs: int, *, add=None):
+    """y[..., :cs] = x[..., c0:c0+cs] (+ add), contiguous."""
+    _dev(x)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    assert x.is_contiguous() and (add is None or (add.is_contiguous() and add.numel() == rows * cs and add.dtype == x.dtype))
+    y = torch.empty(*x.shape[:-1], cs, device=x.device, dtype=x.dtype)
+    with _Timed(0.0, _nb(y) * 2):
+        check(lib.c2d_slice_channels(x.data_ptr(), _ptr(add), y.data_ptr(), rows, C, int(c0), int(cs), _dt(x), _stream()), "slice_channels")
+    return y
+
+
+def mse_loss_grad(pred_nhwc, target_nchw, weight: float, loss_acc):
+    """pred [B,H,W,C] (engine dtype), target fp32 [B,C,H,W]; loss_acc: float64 [1] device accumulator (caller-zeroed).
+    Returns grad [B,H,W,C] (engine dtype) of weight * mse."""
+    _dev(pred_nhwc)
+    B, H, W, C = pred_nhwc.shape
+    assert pred_nhwc.is_contiguous() and target_nchw.is_contiguous() and target_nchw.dtype == torch.float32
+    assert tuple(target_nchw.shape) == (B, C, H, W) and loss_acc.dtype == torch.float64
+    grad = torch.empty_like(pred_nhwc)
+    check(lib.c2d_mse_loss_grad(pred_nhwc.data_ptr(), target_nchw.data_ptr(), grad.data_ptr(), loss_acc.data_ptr(), B, H * W, C,
+                                float(weight), _dt(pred_nhwc), _stream()), "mse_loss_grad")
+    return grad
+
+
+def colsum(x, *, out=None, accumulate: bool = False):
+    """x [B,R,C] -> fp32 [B,C] sums over R."""
+    _dev(x)
+    B, R, C = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(B, C, device=x.device, dtype=torch.float32)
+        accumulate = False
+    check(lib.c2d_colsum(x.data_ptr(), out.data_ptr(), B, R, C, int(accumulate), _dt(x), _stream()), "colsum")
+    return out
+
+
+def gate_bwd(s, af, alpha, dalpha):
+    _dev(s)
+    assert s.dtype == torch.float32 and af.dtype == torch.float32 and s.is_contiguous() and af.is_contiguous() and s.shape == af.shape
+    daf = torch.empty_like(s)
+    check(lib.c2d_gate_bwd(s.data_ptr(), af.data_ptr(), _ptr(_f32(alpha, "alpha")), daf.data_ptr(), dalpha.data_ptr(), s.numel(), _stream()), "gate_bwd")
+    return daf
+
+
+def gelu_bwd_bcast(z, dh, K: int):
+    _dev(z)
+    rows, H = z.shape
+    assert z.dtype == torch.float32 and dh.dtype == torch.float32 and z.is_contiguous() and dh.is_contiguous()
+    assert tuple(dh.shape) == (rows // K, H)
+    dz = torch.empty_like(z)
+    check(lib.c2d_gelu_bwd_bcast(z.data_ptr(), dh.data_ptr(), dz.data_ptr(), rows, H, int(K), _stream()), "gelu_bwd_bcast")
+    return dz
+
+
+def sumsq(x, acc):
+    _dev(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and acc.dtype == torch.float64
+    check(lib.c2d_sumsq(x.data_ptr(), x.numel(), acc.data_ptr(), _stream()), "sumsq")
+    return acc
+
+
+def clip_scale(sumsq_acc, max_norm: float, scale_out, norm_out=None):
+    check(lib.c2d_clip_scale(sumsq_acc.data_ptr(), float(max_norm), scale_out.data_ptr(), _ptr(norm_out), _stream()), "clip_scale")
+    return scale_out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale=None):
+    _dev(param)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    check(lib.c2d_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(), float(lr),
+                             float(beta1), float(beta2), float(eps), float(weight_decay), int(step), _ptr(grad_scale), _stream()), "adamw_step")
+    return param

@@ -154,15 +154,18 @@ class SD15UNet:
     """``SD15UNet(state_dict, device, dtype)``; state-dict keys/shapes are diffusers' (fp32, any device)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", dtype=torch.bfloat16,
-                 impl: int = ops.IMPL_AUTO):
+                 impl: int = ops.IMPL_AUTO, fused: Optional[bool] = None):
+        """fused=False keeps every layer a separate kernel with plain weights (the layout the training step's backward
+        walks, clap2diffusion_b200/train.py); default: all inference fusions on in bf16, off in the fp32 parity mode."""
         self.device = torch.device(device)
         self.dtype = dtype
         self.impl = impl
-        self.fuse_geglu = dtype == torch.bfloat16
-        self.fused_gn = dtype == torch.bfloat16       # producer-side GroupNorm statistics (tcgen05 epilogues)
-        self.fold_ln = dtype == torch.bfloat16        # norm1/2/3 folded into the QKV / to_q / GEGLU GEMMs
-        self.conv_in_tc = dtype == torch.bfloat16     # conv_in on the tensor cores over a channel-padded (4 -> 8) input
-        self.fused_xattn = dtype == torch.bfloat16    # attn2 sites: to_q + attention in one kernel over a packed K/V cache
+        fused = (dtype == torch.bfloat16) if fused is None else (bool(fused) and dtype == torch.bfloat16)
+        self.fuse_geglu = fused
+        self.fused_gn = fused       # producer-side GroupNorm statistics (tcgen05 epilogues)
+        self.fold_ln = fused        # norm1/2/3 folded into the QKV / to_q / GEGLU GEMMs
+        self.conv_in_tc = fused     # conv_in on the tensor cores over a channel-padded (4 -> 8) input
+        self.fused_xattn = fused    # attn2 sites: to_q + attention in one kernel over a packed K/V cache
         self._gn_channels = 0
         self._sd = state_dict
         self.w: Dict[str, torch.Tensor] = {}

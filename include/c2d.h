@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 4   /* 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
+#define C2D_ABI_VERSION 5   /* 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
+                             * 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
                              *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
 enum { C2D_OK = 0, C2D_ERR_ARG = 1, C2D_ERR_CUDA = 2, C2D_ERR_UNSUPPORTED = 3 };
@@ -242,6 +243,52 @@ int c2d_norm_scale(const void* x, void* y, int B, int K, int D, float target, in
  * out[B][nf+nb+na][D] = cat(fg * w0, bg * w1, amb * w2), w = softmax(hierarchy_weights[3]). */
 int c2d_legacy_combine(const void* fg, const void* bg, const void* amb, const float* hierarchy_weights, void* out,
                        int B, int nf, int nb, int na, int D, int dtype, void* stream);
+
+/* ==== stage-3 fine-tune step: backward + optimiser (reference scripts/train_stage3.py:132-191) ==========
+ * With the SD-1.5 UNet frozen the backward pass needs ACTIVATION gradients only.  Dense layers reuse the forward
+ * entry points on transformed copies of the frozen weights (c2d_linear on W^T; c2d_conv3x3 on the flipped + transposed
+ * kernel, after c2d_zero_insert2x for the stride-2 convolutions); the entry points below are the pieces without a
+ * forward twin.  Same dtype switch as the forward kernels, fp32 accumulation.  `add` (optional, same shape as the
+ * output) is summed into the result: the fan-in of residual branches costs no extra pass. */
+/* GroupNorm(+SiLU) adjoint: statistics recomputed from x;  dx = d/dx [act(gn(x))] . dy (+ add) */
+int c2d_group_norm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, int B,
+                       int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
+/* LayerNorm adjoint over the rows of x[M][C] (+ add) */
+int c2d_layer_norm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, int M, int C, float eps,
+                       int dtype, void* stream);
+/* adjoint of c2d_geglu: ag [M][2F] = [a | g], dy [M][F] -> dag [M][2F] */
+int c2d_geglu_bwd(const void* ag, const void* dy, void* dag, int M, int F, int dtype, void* stream);
+/* flash-attention adjoint (recompute form) of c2d_attention: dq, dk, dv from q, k, v, o, dout.  Row strides ld*, batch
+ * strides bs* in elements (packed QKV views welcome); lse_ws / delta_ws: fp32 [B][heads][Nq] scratch each; d <= 160. */
+int c2d_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq, void* dk, void* dv,
+                      float* lse_ws, float* delta_ws, int B, int heads, int Nq, int Nkv, int d, long long ldq, long long ldk,
+                      long long ldv, long long ldo, long long lddo, long long lddq, long long lddk, long long lddv,
+                      long long bsq, long long bsk, long long bsv, long long bso, long long bsdo, long long bsdq,
+                      long long bsdk, long long bsdv, float scale, int dtype, void* stream);
+/* z[B][2H][2W][C]: x at the even positions, zeros elsewhere (adjoint of the stride-2 gather);
+ * y[B][H][W][C] = 2x2 block sums of x[B][2H][2W][C] (adjoint of the nearest 2x upsample);
+ * y[rows][Cs] = x[rows][c0 : c0+Cs] (+ add) (adjoint of the channel concat) */
+int c2d_zero_insert2x(const void* x, void* z, int B, int H, int W, int C, int dtype, void* stream);
+int c2d_sumpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+int c2d_slice_channels(const void* x, const void* add, void* y, long long rows, int C, int c0, int Cs, int dtype, void* stream);
+/* weight * mse(pred, target) and its gradient: pred NHWC [B][HW][C] (dtype), target fp32 NCHW [B][C][HW]; *loss (device
+ * double, caller-zeroed) += the loss, grad (dtype, NHWC) = weight * 2 (pred - target) / n   (train_stage3.py:166) */
+int c2d_mse_loss_grad(const void* pred, const float* target, void* grad, double* loss, int B, int HW, int C, float weight,
+                      int dtype, void* stream);
+/* out fp32 [B][C] (+)= sum over the R rows of x[B][R][C] */
+int c2d_colsum(const void* x, float* out, int B, int R, int C, int accumulate, int dtype, void* stream);
+/* adjoint of  ehs' = ehs + sigmoid(alpha) * af  (audio_attention_processor.py:92-97), fp32, n = B*D:
+ * daf = gate * s,  *dalpha += gate (1 - gate) <s, af>   with s = sum over the text positions of d ehs' */
+int c2d_gate_bwd(const float* s, const float* af, const float* alpha, float* daf, float* dalpha, int n, void* stream);
+/* dz[r][j] = dh[r / K][j] * gelu'(z[r][j]) / K: adjoint of mean-over-K-tokens of gelu(z) (fp32) */
+int c2d_gelu_bwd_bcast(const float* z, const float* dh, float* dz, int rows, int H, int K, void* stream);
+/* optimiser (train_stage3.py:33-38, :182-188): *out (device double, caller-zeroed) += sum x^2;
+ * scale = min(1, max_norm / (sqrt(sumsq) + 1e-6)) as torch.nn.utils.clip_grad_norm_ (norm_out optional);
+ * AdamW (decoupled weight decay, bias correction) on flat fp32 buffers, gradient pre-multiplied by *grad_scale. */
+int c2d_sumsq(const float* x, long long n, double* out, void* stream);
+int c2d_clip_scale(const double* sumsq, float max_norm, float* scale, float* norm_out, void* stream);
+int c2d_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
 
 /* ---- weight packing helpers (run once at load time) ------------------------------------------ */
 /* [Cout][Cin][3][3] fp32 (PyTorch/diffusers layout) -> [Cout][3][3][Cin] dtype */

@@ -400,6 +400,129 @@ def l2_normalize(x, eps=1e-12, *, out=None):
     return F.normalize(x, dim=-1, eps=eps)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# backward / optimiser doubles (stage-3 step).  Each one is torch AUTOGRAD of the forward double -- an independent
+# route to the numbers the hand-written adjoint kernels must produce.
+# ---------------------------------------------------------------------------------------------------------
+def _vjp(fn, inputs, gy):
+    xs = [t.detach().float().requires_grad_(True) for t in inputs]
+    with torch.enable_grad():
+        y = fn(*xs)
+        return torch.autograd.grad(y, xs, gy.float().reshape(y.shape))
+
+
+def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None):
+    B, C = x.shape[0], x.shape[-1]
+
+    def f(t):
+        y = F.group_norm(t.reshape(B, -1, C).transpose(1, 2), groups, gamma.float(), beta.float(), eps).transpose(1, 2)
+        return (F.silu(y) if silu else y).reshape(x.shape)
+    g = _vjp(f, [x], dy)[0]
+    if add is not None:
+        g = g + add.float()
+    return g.to(x.dtype)
+
+
+def layer_norm_bwd(x, dy, gamma, eps=1e-5, *, add=None, out=None):
+    g = _vjp(lambda t: F.layer_norm(t, (x.shape[-1],), gamma.float(), torch.zeros_like(gamma).float(), eps), [x], dy)[0]
+    if add is not None:
+        g = g + add.float()
+    return g.to(x.dtype)
+
+
+def geglu_bwd(ag, dy, *, out=None):
+    Fh = dy.shape[-1]
+    return _vjp(lambda t: t[..., :Fh] * F.gelu(t[..., Fh:]), [ag], dy)[0].to(ag.dtype)
+
+
+def attention_bwd(q, k, v, o, dout, heads, dq, dk, dv, *, scale=None):
+    def f(qq, kk, vv):
+        B, Nq, C = qq.shape
+        d = C // heads
+        sc = d ** -0.5 if scale is None else scale
+        qh = qq.reshape(B, Nq, heads, d).transpose(1, 2)
+        kh = kk.reshape(B, -1, heads, d).transpose(1, 2)
+        vh = vv.reshape(B, -1, heads, d).transpose(1, 2)
+        return (torch.softmax(qh @ kh.transpose(-1, -2) * sc, -1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+    gq, gk, gv = _vjp(f, [q, k, v], dout)
+    dq.copy_(gq); dk.copy_(gk); dv.copy_(gv)
+    return dq, dk, dv
+
+
+def zero_insert2x(x):
+    B, H, W, C = x.shape
+    z = torch.zeros(B, 2 * H, 2 * W, C, dtype=x.dtype)
+    z[:, ::2, ::2] = x
+    return z
+
+
+def sumpool2x2(x):
+    B, H2, W2, C = x.shape
+    return x.float().reshape(B, H2 // 2, 2, W2 // 2, 2, C).sum(dim=(2, 4)).to(x.dtype)
+
+
+def slice_channels(x, c0, cs, *, add=None):
+    y = x[..., c0:c0 + cs].float()
+    if add is not None:
+        y = y + add.float().reshape(y.shape)
+    return y.contiguous().to(x.dtype)
+
+
+def mse_loss_grad(pred_nhwc, target_nchw, weight, loss_acc):
+    p = pred_nhwc.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        loss = weight * F.mse_loss(p.permute(0, 3, 1, 2), target_nchw.float())
+        g = torch.autograd.grad(loss, p)[0]
+    loss_acc += loss.detach().double()
+    return g.to(pred_nhwc.dtype)
+
+
+def colsum(x, *, out=None, accumulate=False):
+    s = x.float().sum(1)
+    if out is None:
+        return s
+    if accumulate:
+        out += s.reshape(out.shape)
+    else:
+        out.copy_(s.reshape(out.shape))
+    return out
+
+
+def gate_bwd(s, af, alpha, dalpha):
+    gate = torch.sigmoid(alpha.float().reshape(()))
+    dalpha += (s * af).sum() * gate * (1 - gate)
+    return gate * s
+
+
+def gelu_bwd_bcast(z, dh, K):
+    zz = z.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        g = torch.autograd.grad(F.gelu(zz), zz, dh.repeat_interleave(K, 0) / K)[0]
+    return g
+
+
+def sumsq(x, acc):
+    acc += (x.double() ** 2).sum()
+    return acc
+
+
+def clip_scale(sumsq_acc, max_norm, scale_out, norm_out=None):
+    norm = float(sumsq_acc.reshape(-1)[0]) ** 0.5
+    scale_out.fill_(min(1.0, max_norm / (norm + 1e-6)))
+    if norm_out is not None:
+        norm_out.fill_(norm)
+    return scale_out
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+    g = grad * (1.0 if grad_scale is None else float(grad_scale.reshape(-1)[0]))
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    param.addcdiv_(exp_avg / (1 - beta1 ** step), (exp_avg_sq / (1 - beta2 ** step)).sqrt() + eps, value=-lr)
+    return param
+
+
 def require_cuda(x, who):
     """The CPU host-logic tests run the product's launch sequences on torch doubles: no device requirement."""
     return None

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Stage-3 step probe (GPU): one forward_backward in the given dtype at a small latent; CUDA_LAUNCH_BLOCKING=1 localises faults."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+from oracle import pipeline as PL  # noqa: E402
+from test_train_host_logic import make_batch  # noqa: E402
+from clap2diffusion_b200 import ops  # noqa: E402
+from clap2diffusion_b200.models.hierarchical_audio_v4 import ImprovedHierarchicalAudioEncoder  # noqa: E402
+from clap2diffusion_b200.train import LEVELS, Stage3Trainer  # noqa: E402
+
+dt = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else torch.float32
+hw = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+W = PL.build_weights(seed=0, with_vae=False)
+hier = ImprovedHierarchicalAudioEncoder().to("cuda").eval()
+hier.load_state_dict({k: v.to("cuda") for k, v in W["hier"].items()})
+tr = Stage3Trainer(W["unet"], hier, {l: W[f"proc_{l}"] for l in LEVELS}, device="cuda", dtype=dt)
+batch = make_batch(B=min(B, 4), h=hw, w=hw)
+if B > 4:
+    batch = {k: v.repeat(*( [B // 4] + [1] * (v.dim() - 1))) for k, v in make_batch(B=4, h=hw, w=hw).items()}
+torch.cuda.synchronize()
+for i in range(3):
+    t0 = time.time()
+    out = tr.train_step(batch)
+    torch.cuda.synchronize()
+    print(f"step {i}: loss {float(out['diffusion']):.6f} grad_norm {float(out['grad_norm']):.4e}  {1e3 * (time.time() - t0):.1f} ms")
+ops.PROFILE = []
+tr.train_step(batch)
+torch.cuda.synchronize()
+rec, ops.PROFILE = ops.PROFILE, None
+agg = {}
+for name, fl, nb, e0, e1 in rec:
+    a = agg.setdefault(name, [0.0, 0])
+    a[0] += e0.elapsed_time(e1); a[1] += 1
+tot = sum(a[0] for a in agg.values())
+print(f"timed ops total {tot:.2f} ms")
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
+    print(f"  {k:20s} {a[0]:8.3f} ms x{a[1]}")
