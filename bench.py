@@ -294,6 +294,81 @@ def run_clap(args):
                                    "note": "short-K GEMMs (C = 96 .. 768) and an fp32 DFT GEMM: far from the dense-bf16 roof by construction"}}))
 
 
+def run_train(args):
+    """`--train`: BASELINE config 5 -- the stage-3 fine-tune step (audio attention processors trainable, SD-1.5 UNet
+    frozen), data-parallel with `--train-batch` samples per GPU (4 x 8 GPUs = the config's global batch 32), 64 x 64
+    latents, bf16.  A "step" = forward + hand-written backward through the frozen UNet + per-level all-reduce buckets +
+    clip + AdamW.  Prints one JSON line (samples/s over all ranks, device-timed, max over ranks)."""
+    import contextlib
+    import torch.distributed as dist
+    from clap2diffusion_b200 import _lib, synthetic
+    from clap2diffusion_b200 import unet as unet_mod
+    from clap2diffusion_b200.models.hierarchical_audio_v4 import ImprovedHierarchicalAudioEncoder
+    from clap2diffusion_b200.train import Stage3Trainer
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --train: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.train_batch
+    with contextlib.redirect_stdout(sys.stderr):
+        usd = synthetic.random_state_dict(unet_mod.param_shapes(), 0, dev)
+        hier = ImprovedHierarchicalAudioEncoder().to(dev).eval()
+        tr = Stage3Trainer(usd, hier, None, device=dev, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(1234 + rank)
+
+    def batch(i):
+        ids = [(rank * 100003 + i) * b + j for j in range(b)]
+        return {"audio_embedding": torch.from_numpy(np.stack([synthetic.clap_embedding(k) for k in ids])),
+                "image_latents": torch.randn(b, 4, LATENT, LATENT, generator=g),
+                "text_embedding": torch.from_numpy(np.stack([synthetic.text_states(f"prompt {k % 8}") for k in ids])),
+                "noise": torch.randn(b, 4, LATENT, LATENT, generator=g),
+                "timesteps": torch.randint(0, 1000, (b,), generator=g)}
+
+    batches = [{k: v.to(dev) for k, v in batch(i).items()} for i in range(4)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 1)):
+        tr.train_step(batches[i % 4])
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = tr.train_step(batches[i % 4])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    flat = tr.flat.clone()
+    same = True
+    if world > 1:                               # replicas must hold bit-identical parameters after the steps
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(int(ok))
+    if rank == 0:
+        msv = float(ms) / args.steps
+        print(json.dumps({"metric": "stage3_train_samples_per_sec", "value": world * b / (msv * 1e-3), "unit": "samples/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": msv, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"config 5: stage-3 fine-tune step, audio attention processors trainable (297,411 parameters), "
+                                                 f"SD-1.5 UNet frozen, {b} samples/GPU (global batch {world * b}), 64x64 latents, DDP over {world} GPU(s)",
+                                     "per_gpu_batch": b},
+                          "gpu_launches": int(_lib.launch_count() - l0), "replicas_identical": same,
+                          "loss": float(out["diffusion"]) * world, "grad_norm": float(out["grad_norm"])}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _xattn_evidence(agg):
     """The north star's named kernel: live CUDA-event time of the 16 fused cross-attention launches of one step (the
     persistent weight-stationary kernel at the C = 320 sites, the first-generation kernel elsewhere) plus the
@@ -532,8 +607,12 @@ def main():
     ap.add_argument("--clips", type=int, default=256)
     ap.add_argument("--vae", action="store_true", help="with --kernels: also time the VAE decoder")
     ap.add_argument("--ncu-step", action="store_true", help="profile one eager UNet step (for ncu --profile-from-start off)")
+    ap.add_argument("--train", action="store_true", help="config 5: stage-3 fine-tune step throughput (samples/s)")
+    ap.add_argument("--train-batch", type=int, default=4, help="with --train: samples per GPU (4 x 8 GPUs = global batch 32)")
     args = ap.parse_args()
-    if args.clap:
+    if args.train:
+        run_train(args)
+    elif args.clap:
         run_clap(args)
     elif args.ncu_step:
         run_ncu_step(args)
