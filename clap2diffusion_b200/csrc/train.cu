@@ -580,6 +580,18 @@ static int attention_bwd_t(const AttnBwdParams& p, int B, cudaStream_t s) {
   return attention_bwd_n<T, AB_MAXD / 16>(p, B, s);          // d <= 160
 }
 
+// attn_bwd_tc.cu: tcgen05 kernels (bf16, head dims up to 128)
+struct AttnBwdArgs {
+  const void *q, *k, *v, *o, *dout;
+  void *dq, *dk, *dv;
+  float *lse, *delta;
+  int B, heads, Nq, Nkv, d;
+  long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv;
+  float scale;
+};
+bool attention_bwd_tc_supported(const AttnBwdArgs& a);
+int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t s);
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -635,7 +647,12 @@ int c2d_attention_bwd(const void* q, const void* k, const void* v, const void* o
   AttnBwdParams p = {q, k, v, o, dout, dq, dk, dv, lse_ws, delta_ws, Nq, Nkv, d, heads,
                      ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv, scale};
   if (dtype == C2D_F32) return attention_bwd_t<float>(p, B, (cudaStream_t)stream);
-  if (dtype == C2D_BF16) return attention_bwd_t<bf16>(p, B, (cudaStream_t)stream);
+  if (dtype == C2D_BF16) {
+    const AttnBwdArgs a = {q, k, v, o, dout, dq, dk, dv, lse_ws, delta_ws, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
+                           lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv, scale};
+    if (attention_bwd_tc_supported(a)) return attention_bwd_tc(a, (cudaStream_t)stream);      // tensor cores
+    return attention_bwd_t<bf16>(p, B, (cudaStream_t)stream);                                 // head dims > 128: FFMA kernels
+  }
   set_error("attention_bwd: bad dtype %d", dtype);
   return C2D_ERR_ARG;
 }
