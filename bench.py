@@ -313,6 +313,7 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     b = args.train_batch
+    torch.manual_seed(0)                     # the frozen projector / decomposer is the same random init on every rank
     with contextlib.redirect_stdout(sys.stderr):
         usd = synthetic.random_state_dict(unet_mod.param_shapes(), 0, dev)
         hier = ImprovedHierarchicalAudioEncoder().to(dev).eval()

@@ -341,6 +341,10 @@ class Stage3Trainer:
         self.world = 1
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
+        if self.world > 1:
+            # DDP semantics: every replica starts from rank 0's parameters (the processors' tensors are views of `flat`)
+            torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._time_table: Optional[torch.Tensor] = None      # [1000, sum(Cout)] rows of SD15UNet.time_table, built on first use
         self.step_count = 0
         self._scalars = torch.zeros(4, device=self.device, dtype=torch.float32)       # [clip scale, grad norm, -, -]
         self._acc = torch.zeros(2, device=self.device, dtype=torch.float64)           # [loss, sum of squares]
@@ -403,7 +407,12 @@ class Stage3Trainer:
         noise = noise.to(dev).float().contiguous()
         noisy = (a * latents.to(dev).float() + (1.0 - a) * noise).contiguous()
         x = ops.nchw_to_nhwc(noisy, dt)
-        temb_rows = self.unet.time_table([float(v) for v in t.tolist()])
+        # time-embedding rows: the time MLP and the 22 time_emb_proj layers are frozen, so the whole table of the 1000
+        # training timesteps is evaluated once (82 MB fp32) and a step only gathers its B rows
+        if self._time_table is None:
+            self._time_table = torch.cat([self.unet.time_table([float(v) for v in range(i, min(i + 250, 1000))])
+                                          for i in range(0, 1000, 250)], 0)
+        temb_rows = self._time_table.index_select(0, timesteps.to(dev).long().clamp(0, 999))
         # forward with the tape, loss, adjoint
         tp = _Tape()
         pending = {lvl: sum(1 for v in self.level_of.values() if v == lvl) for lvl in LEVELS}

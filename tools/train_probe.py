@@ -31,6 +31,12 @@ for i in range(3):
     out = tr.train_step(batch)
     torch.cuda.synchronize()
     print(f"step {i}: loss {float(out['diffusion']):.6f} grad_norm {float(out['grad_norm']):.4e}  {1e3 * (time.time() - t0):.1f} ms")
+if os.environ.get("C2D_PROFILE"):            # one step between cudaProfilerStart / Stop (ncu --profile-from-start off)
+    torch.cuda.profiler.start()
+    tr.train_step(batch)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 ops.PROFILE = []
 tr.train_step(batch)
 torch.cuda.synchronize()
