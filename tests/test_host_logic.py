@@ -445,3 +445,23 @@ def test_clap_mel_filter_bank_and_feature_config(tmp_path):
     cfg = CLAPAudioEncoder._feature_config(str(tmp_path), None)
     assert (cfg["frequency_min"], cfg["frequency_max"]) == (30.0, 13000.0) and cfg["source"].endswith("preprocessor_config.json")
     assert CLAPAudioEncoder._feature_config(str(tmp_path), {"frequency_min": 10})["frequency_min"] == 10.0
+
+
+def test_evaluate_and_gradio_surface_without_gpu():
+    """Class / method / CLI names of the reference's evaluate.py and gradio_app.py (no device work)."""
+    import importlib.util
+    import inspect
+    import os
+    root = os.path.join(os.path.dirname(__file__), "..")
+    for name, path, cls, methods in (("ev", "scripts/evaluate.py", "Evaluator", ("compute_clip_score", "compute_audio_alignment", "evaluate_single",
+                                                                                  "evaluate_dataset", "print_results")),
+                                     ("gr", "app/gradio_app.py", "AudioToImageGenerator", ("load_models", "generate"))):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, path))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        c = getattr(mod, cls)
+        for m in methods:
+            assert callable(getattr(c, m))
+        assert callable(mod.main)
+    sig = inspect.signature(mod.AudioToImageGenerator.generate)
+    assert list(sig.parameters)[1:] == ["audio_path", "text_prompt", "norm_value", "num_steps", "cfg_scale", "seed", "model_type"]
