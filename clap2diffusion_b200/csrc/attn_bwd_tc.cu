@@ -17,6 +17,9 @@
 //       of dV += P^T dO and dK += dS^T Q (M = keys, K = queries); dO / Q tiles serve as K-major A operands of the score
 //       MMAs and as MN-major B operands of the accumulations from the same shared-memory image.
 // TMEM: S 128 | dP 128 | accumulators 64 * NBLK (dQ) or 2 x 64 * NBLK (dV, dK) columns.
+// Head dims 129..192 (the 1280-channel levels: d = 160) run the dQ kernel with NBLK = 3 as is; the dK / dV kernel would
+// need 640 TMEM columns and 256 KB of shared memory there, so it is launched twice (MODE 1: dV only -- S, no V; MODE 2:
+// dK only), one extra score GEMM on layers that hold 1 / 16 of the tokens.
 // Recomputing S / dP in both kernels costs 2 extra GEMMs of 7; it avoids fp32 atomics on dQ and a dQ conversion pass.
 #include <float.h>
 
@@ -307,22 +310,26 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ================================================================================================ dK, dV
-template <int NBLK>
+template <int NBLK, int MODE>                                  // MODE 0: dV and dK, 1: dV only, 2: dK only
 struct BwKCfg {
+  static constexpr bool HAS_V = MODE != 1, HAS_P = MODE != 2, HAS_DS = MODE != 1;
   static constexpr int QS = NBLK == 1 ? 2 : 1;                 // Q / dO ring depth
   static constexpr int TILE = NBLK * BW_BLK;
-  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = OFF_Q + QS * TILE;
-  static constexpr int OFF_P = OFF_DO + QS * TILE, OFF_DS = OFF_P + 2 * BW_BLK;
-  static constexpr int OFF_BAR = OFF_DS + 2 * BW_BLK;
+  static constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = HAS_V ? 2 * TILE : TILE, OFF_DO = OFF_Q + QS * TILE;
+  static constexpr int OFF_P = OFF_DO + QS * TILE, OFF_DS = OFF_P + (HAS_P ? 2 * BW_BLK : 0);
+  static constexpr int OFF_BAR = OFF_DS + (HAS_DS ? 2 * BW_BLK : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "attention backward: shared memory");
+  static_assert(256 + (MODE == 0 ? 2 : 1) * 64 * NBLK <= 512, "attention backward: TMEM columns");
 };
 
-template <int NBLK>
+template <int NBLK, int MODE>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const BwParams p) {
-  using Cfg = BwKCfg<NBLK>;
+  using Cfg = BwKCfg<NBLK, MODE>;
   constexpr int QS = Cfg::QS;
+  constexpr bool HAS_V = Cfg::HAS_V, HAS_P = Cfg::HAS_P, HAS_DS = Cfg::HAS_DS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -355,16 +362,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128;
-  const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 256 + 64 * NBLK;
+  const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 256 + (MODE == 0 ? 64 * NBLK : 0);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(kv_full, 2 * Cfg::TILE);
+      mbar_arrive_expect_tx(kv_full, (HAS_V ? 2 : 1) * Cfg::TILE);
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
         tma_load_4d(smem + Cfg::OFF_K + blk * BW_BLK, &tmK, kv_full, blk * 64, h, k0, b);
-        tma_load_4d(smem + Cfg::OFF_V + blk * BW_BLK, &tmV, kv_full, blk * 64, h, k0, b);
+        if (HAS_V) tma_load_4d(smem + Cfg::OFF_V + blk * BW_BLK, &tmV, kv_full, blk * 64, h, k0, b);
       }
     }
     __syncwarp();
@@ -394,15 +401,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int s = i % QS;
       const uint64_t do_mn = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_DO + s * Cfg::TILE), BW_BLK, 1024);
       const uint64_t q_mn = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_Q + s * Cfg::TILE), BW_BLK, 1024);
+      if (HAS_P) {
 #pragma unroll
-      for (int kk = 0; kk < BW_T / 16; ++kk) {
-        const uint64_t off = (uint64_t)(kk * (2048 >> 4));
-        umma_f16(tmem_dv, p_desc + off, do_mn + off, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < BW_T / 16; ++kk) {
+          const uint64_t off = (uint64_t)(kk * (2048 >> 4));
+          umma_f16(tmem_dv, p_desc + off, do_mn + off, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
       }
+      if (HAS_DS) {
 #pragma unroll
-      for (int kk = 0; kk < BW_T / 16; ++kk) {
-        const uint64_t off = (uint64_t)(kk * (2048 >> 4));
-        umma_f16(tmem_dk, ds_desc + off, q_mn + off, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < BW_T / 16; ++kk) {
+          const uint64_t off = (uint64_t)(kk * (2048 >> 4));
+          umma_f16(tmem_dk, ds_desc + off, q_mn + off, idesc_acc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
       }
       umma_commit(pds_free);
       umma_commit(&qo_empty[s]);
@@ -425,10 +436,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const uint64_t off = (uint64_t)((kk >> 2) * (BW_BLK >> 4) + (kk & 3) * 2);
           umma_f16(tmem_s, qd + off, k_desc + off, idesc_s, kk > 0 ? 1u : 0u);
         }
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t off = (uint64_t)((kk >> 2) * (BW_BLK >> 4) + (kk & 3) * 2);
-          umma_f16(tmem_dp, dd + off, v_desc + off, idesc_s, kk > 0 ? 1u : 0u);
-        }
+        if (HAS_DS)
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t off = (uint64_t)((kk >> 2) * (BW_BLK >> 4) + (kk & 3) * 2);
+            umma_f16(tmem_dp, dd + off, v_desc + off, idesc_s, kk > 0 ? 1u : 0u);
+          }
         umma_commit(sd_full);
       }
       __syncwarp();
@@ -465,7 +477,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int cc = 0; cc < BW_T; cc += 32) {
         uint32_t rs[32], rd[32];
         tmem_ld_32x32(tmem_s + lane_off + (uint32_t)cc, rs);
-        tmem_ld_32x32(tmem_dp + lane_off + (uint32_t)cc, rd);
+        if (HAS_DS) tmem_ld_32x32(tmem_dp + lane_off + (uint32_t)cc, rd);
         tmem_ld_wait();
         uint32_t pp[16], pd[16];
 #pragma unroll
@@ -473,8 +485,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           float p0 = 0.f, p1 = 0.f;
           if (row_ok && cc + j < kvalid) p0 = bw_ex2(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lse));
           if (row_ok && cc + j + 1 < kvalid) p1 = bw_ex2(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lse));
-          pp[j >> 1] = bw_pack(p0, p1);
-          pd[j >> 1] = bw_pack(p0 * (__uint_as_float(rd[j]) - dl) * p.scale, p1 * (__uint_as_float(rd[j + 1]) - dl) * p.scale);
+          if (HAS_P) pp[j >> 1] = bw_pack(p0, p1);
+          if (HAS_DS) pd[j >> 1] = bw_pack(p0 * (__uint_as_float(rd[j]) - dl) * p.scale, p1 * (__uint_as_float(rd[j + 1]) - dl) * p.scale);
         }
         // keys [cc, cc + 32) of this query row: 64-key block cc / 64, 16-byte chunks (cc % 64) / 8 .. + 3, swizzled by the row
         const uint32_t blk = (uint32_t)(cc >> 6) * (uint32_t)BW_BLK;
@@ -482,8 +494,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t off = blk + (((ch0 + q) ^ sw) << 4);
-          bw_sts128(p_row + off, pp[q * 4], pp[q * 4 + 1], pp[q * 4 + 2], pp[q * 4 + 3]);
-          bw_sts128(ds_row + off, pd[q * 4], pd[q * 4 + 1], pd[q * 4 + 2], pd[q * 4 + 3]);
+          if (HAS_P) bw_sts128(p_row + off, pp[q * 4], pp[q * 4 + 1], pp[q * 4 + 2], pp[q * 4 + 3]);
+          if (HAS_DS) bw_sts128(ds_row + off, pd[q * 4], pd[q * 4 + 1], pd[q * 4 + 2], pd[q * 4 + 3]);
         }
       }
       tc_fence_before();
@@ -494,8 +506,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tc_fence_after();
     const int krow = k0 + row;
     const bool ok = krow < p.Nkv;
-    bw_store_acc(tmem_dv + lane_off, p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + (long long)h * p.d, ok, p.d, p.npv);
-    bw_store_acc(tmem_dk + lane_off, p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + (long long)h * p.d, ok, p.d, p.npv);
+    if (HAS_P)
+      bw_store_acc(tmem_dv + lane_off, p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + (long long)h * p.d, ok, p.d, p.npv);
+    if (HAS_DS)
+      bw_store_acc(tmem_dk + lane_off, p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + (long long)h * p.d, ok, p.d, p.npv);
   }
   tc_fence_before();
   __syncthreads();
@@ -533,7 +547,7 @@ bool attention_bwd_tc_supported(const AttnBwdArgs& a) {
   const long long strides[] = {a.ldq, a.ldk, a.ldv, a.ldo, a.lddo, a.lddq, a.lddk, a.lddv, a.bsq, a.bsk, a.bsv, a.bso, a.bsdo, a.bsdq, a.bsdk, a.bsdv};
   for (long long s : strides)
     if (s % 8) return false;
-  return enabled && a.d % 8 == 0 && a.d >= 16 && a.d <= 128 && bw_al16(a.q) && bw_al16(a.k) && bw_al16(a.v) && bw_al16(a.o) &&
+  return enabled && a.d % 8 == 0 && a.d >= 16 && a.d <= 192 && bw_al16(a.q) && bw_al16(a.k) && bw_al16(a.v) && bw_al16(a.o) &&
          bw_al16(a.dout) && bw_al16(a.dq) && bw_al16(a.dk) && bw_al16(a.dv) && (a.B == 1 || (a.bsq > 0 && a.bsk > 0 && a.bsv > 0 && a.bsdo > 0));
 }
 
@@ -545,12 +559,21 @@ static int attention_bwd_tc_n(const AttnBwdArgs& a, const BwParams& p, cudaStrea
   if ((rc = bw_head_tmap(&tk, a.k, a.d, a.heads, a.Nkv, a.B, a.ldk, a.bsk))) return rc;
   if ((rc = bw_head_tmap(&tv, a.v, a.d, a.heads, a.Nkv, a.B, a.ldv, a.bsv))) return rc;
   if ((rc = bw_head_tmap(&td, a.dout, a.d, a.heads, a.Nq, a.B, a.lddo, a.bsdo))) return rc;
-  static int set_q[C2D_MAX_DEVICES] = {}, set_k[C2D_MAX_DEVICES] = {};
+  static int set_q[C2D_MAX_DEVICES] = {}, set_k[C2D_MAX_DEVICES] = {}, set_k2[C2D_MAX_DEVICES] = {};
   if ((rc = ensure_dyn_smem(attn_bwd_dq_tc_kernel<NBLK>, BwQCfg<NBLK>::SMEM_BYTES, set_q, "attention_bwd_tc"))) return rc;
-  if ((rc = ensure_dyn_smem(attn_bwd_dkv_tc_kernel<NBLK>, BwKCfg<NBLK>::SMEM_BYTES, set_k, "attention_bwd_tc"))) return rc;
   attn_bwd_dq_tc_kernel<NBLK><<<dim3(ceil_div(a.Nq, BW_T), a.heads, a.B), BW_THREADS, BwQCfg<NBLK>::SMEM_BYTES, s>>>(tq, tk, tv, td, p);
   if ((rc = check_launch("attention_bwd_tc"))) return rc;
-  attn_bwd_dkv_tc_kernel<NBLK><<<dim3(ceil_div(a.Nkv, BW_T), a.heads, a.B), BW_THREADS, BwKCfg<NBLK>::SMEM_BYTES, s>>>(tq, tk, tv, td, p);
+  const dim3 kgrid(ceil_div(a.Nkv, BW_T), a.heads, a.B);
+  if constexpr (NBLK <= 2) {
+    if ((rc = ensure_dyn_smem(attn_bwd_dkv_tc_kernel<NBLK, 0>, BwKCfg<NBLK, 0>::SMEM_BYTES, set_k, "attention_bwd_tc"))) return rc;
+    attn_bwd_dkv_tc_kernel<NBLK, 0><<<kgrid, BW_THREADS, BwKCfg<NBLK, 0>::SMEM_BYTES, s>>>(tq, tk, tv, td, p);
+  } else {
+    if ((rc = ensure_dyn_smem(attn_bwd_dkv_tc_kernel<NBLK, 1>, BwKCfg<NBLK, 1>::SMEM_BYTES, set_k, "attention_bwd_tc"))) return rc;
+    if ((rc = ensure_dyn_smem(attn_bwd_dkv_tc_kernel<NBLK, 2>, BwKCfg<NBLK, 2>::SMEM_BYTES, set_k2, "attention_bwd_tc"))) return rc;
+    attn_bwd_dkv_tc_kernel<NBLK, 1><<<kgrid, BW_THREADS, BwKCfg<NBLK, 1>::SMEM_BYTES, s>>>(tq, tk, tv, td, p);
+    if ((rc = check_launch("attention_bwd_tc"))) return rc;
+    attn_bwd_dkv_tc_kernel<NBLK, 2><<<kgrid, BW_THREADS, BwKCfg<NBLK, 2>::SMEM_BYTES, s>>>(tq, tk, tv, td, p);
+  }
   return check_launch("attention_bwd_tc");
 }
 
@@ -563,7 +586,8 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t s) {
   p.lddq = a.lddq; p.bsdq = a.bsdq; p.lddk = a.lddk; p.bsdk = a.bsdk; p.lddv = a.lddv; p.bsdv = a.bsdv;
   p.ldo = a.ldo; p.bso = a.bso; p.lddo = a.lddo; p.bsdo = a.bsdo;
   p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
-  return a.d <= 64 ? attention_bwd_tc_n<1>(a, p, s) : attention_bwd_tc_n<2>(a, p, s);
+  if (a.d <= 64) return attention_bwd_tc_n<1>(a, p, s);
+  return a.d <= 128 ? attention_bwd_tc_n<2>(a, p, s) : attention_bwd_tc_n<3>(a, p, s);
 }
 
 }  // namespace c2d

@@ -340,6 +340,135 @@ static void gn2_grid(int B, int HW, int rif, dim3* grid, int* rows_per_cta) {
   *grid = dim3(ceil_div(HW, rpc), B);
 }
 
+// ---- GroupNorm(+SiLU) backward, bf16 fast path (training step): three coalesced passes with the channel-vector
+// mapping of gn_apply2 instead of one CTA per (sample, group) walking a strided slab.
+//   pass 1  chan_stats_kernel: per-channel (sum x, sum x^2) -> group mean / rstd
+//   pass 2  gn_bwd_reduce_kernel: g = dy * act'(z) * gamma; per-channel (sum g, sum g * xhat) -> double atomics
+//   pass 3  gn_bwd_apply_kernel: dx = rstd * (g - mean_group(g) - xhat * mean_group(g * xhat)) (+ add)
+// Group statistics of both kinds are rebuilt per CTA from the per-channel arrays (one warp per group).
+__device__ __forceinline__ void gnb_group_stats(const long long* __restrict__ st, const double* __restrict__ gst, int b, int C,
+                                                int groups, int HW, float eps, float* s_mean, float* s_rstd, float* s_m1,
+                                                float* s_m2) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, cpg = C / groups;
+  for (int g = warp; g < groups; g += nwarps) {
+    long long a = 0, q = 0;
+    double g1 = 0.0, g2 = 0.0;
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      const long long* sp = st + ((long long)b * C + c) * 2;
+      a += sp[0]; q += sp[1];
+      if (gst) { g1 += gst[((long long)b * C + c) * 2]; g2 += gst[((long long)b * C + c) * 2 + 1]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+      g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+      g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+    }
+    if (lane == 0) {
+      const double inv_n = 1.0 / ((double)HW * (double)cpg);
+      const double mean = (double)a * STATS_INV_SCALE * inv_n;
+      double var = (double)q * STATS_INV_SCALE * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+      if (gst) { s_m1[g] = (float)(g1 * inv_n); s_m2[g] = (float)(g2 * inv_n); }
+    }
+  }
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(GN2_MAX_THREADS, 2)
+gn_bwd_pass_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const long long* __restrict__ st, double* __restrict__ gst,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const bf16* __restrict__ add, bf16* __restrict__ dx,
+                   int HW, int C, int groups, float eps, int silu, int rows_per_cta) {
+  const int nvec = C >> 3, cpg = C / groups;
+  const int b = blockIdx.y;
+  const int rif = blockDim.x / nvec;
+  const int my_vec = threadIdx.x % nvec, my_rl = threadIdx.x / nvec;
+  const int c0 = my_vec * 8;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS], s_m1[GN_MAX_GROUPS], s_m2[GN_MAX_GROUPS];
+  gnb_group_stats(st, APPLY ? gst : nullptr, b, C, groups, HW, eps, s_mean, s_rstd, s_m1, s_m2);
+  __syncthreads();
+  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j, g = c / cpg;
+    mean[j] = s_mean[g]; rstd[j] = s_rstd[g];
+    ga[j] = __ldg(gamma + c); be[j] = __ldg(beta + c);
+    m1[j] = APPLY ? s_m1[g] : 0.f; m2[j] = APPLY ? s_m2[g] : 0.f;
+  }
+  const long long base = (long long)b * HW * C + c0;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+  for (int r = r0 + my_rl; r < r1; r += rif) {
+    const long long o = base + (long long)r * C;
+    float fx[8], fd[8];
+    Vec8<bf16>::load(x + o, fx);
+    Vec8<bf16>::load(dy + o, fd);
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (fx[j] - mean[j]) * rstd[j];
+      float d = fd[j];
+      if (silu) {
+        const float z = fmaf(ga[j], xh, be[j]);
+        const float sg = 1.f / (1.f + __expf(-z));
+        d *= sg * (1.f + z * (1.f - sg));
+      }
+      const float gg = d * ga[j];
+      if (APPLY) out[j] = rstd[j] * (gg - m1[j] - xh * m2[j]);
+      else { a1[j] += gg; a2[j] = fmaf(gg, xh, a2[j]); }
+    }
+    if (APPLY) {
+      if (add) {
+        float fa[8];
+        Vec8<bf16>::load(add + o, fa);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] += fa[j];
+      }
+      Vec8<bf16>::store(dx + o, out);
+    }
+  }
+  if (!APPLY) {
+    extern __shared__ float s_part[];            // [rif][C][2]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[((size_t)my_rl * C + c0 + j) * 2 + 0] = a1[j];
+      s_part[((size_t)my_rl * C + c0 + j) * 2 + 1] = a2[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int rl = 0; rl < rif; ++rl) t += s_part[(size_t)rl * C * 2 + i];
+      atomicAdd(gst + (size_t)b * C * 2 + i, (double)t);
+    }
+  }
+}
+
+// ws: caller-zeroed, B * C * 2 int64 (channel statistics of x) followed by B * C * 2 doubles (adjoint sums)
+int group_norm_bwd_fast(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
+                        int B, int HW, int C, int groups, float eps, int silu, cudaStream_t s) {
+  const int threads = gn2_threads(C), rif = threads / (C / 8);
+  dim3 grid;
+  int rpc;
+  gn2_grid(B, HW, rif, &grid, &rpc);
+  const size_t smem = (size_t)rif * C * 2 * sizeof(float);
+  if (smem > 48 * 1024) return -1;
+  long long* st = reinterpret_cast<long long*>(ws);
+  double* gst = reinterpret_cast<double*>(st + (size_t)B * C * 2);
+  chan_stats_kernel<bf16><<<grid, threads, smem, s>>>((const bf16*)x, reinterpret_cast<unsigned long long*>(st), HW, C, rpc);
+  if (int rc = check_launch("group_norm_bwd")) return rc;
+  gn_bwd_pass_kernel<false><<<grid, threads, smem, s>>>((const bf16*)x, (const bf16*)dy, st, gst, gamma, beta, nullptr, nullptr, HW, C,
+                                                        groups, eps, silu, rpc);
+  if (int rc = check_launch("group_norm_bwd")) return rc;
+  gn_bwd_pass_kernel<true><<<grid, threads, 0, s>>>((const bf16*)x, (const bf16*)dy, st, gst, gamma, beta, (const bf16*)add, (bf16*)dx, HW,
+                                                    C, groups, eps, silu, rpc);
+  return check_launch("group_norm_bwd");
+}
+
 // ---- LayerNorm: one warp handles ROWS rows at once (ROWS x ITERS independent 128-bit loads in flight per lane),
 // rows kept in registers, two-pass statistics in registers.  C % 8 == 0 and C <= 256 * ITERS.
 template <typename T, int ITERS, int ROWS>

@@ -780,9 +780,12 @@ def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=N
     assert add is None or (add.is_contiguous() and add.shape == x.shape and add.dtype == x.dtype)
     if out is None:
         out = torch.empty_like(x)
+    # scratch of the three-pass bf16 path: int64 channel statistics + double adjoint sums, zeroed per call
+    ws = torch.zeros(B * C * 4, device=x.device, dtype=torch.int64) if x.dtype == torch.bfloat16 and C % 8 == 0 else None
     with _Timed(0.0, 5 * _nb(x) + _nb(out)):
         check(lib.c2d_group_norm_bwd(x.data_ptr(), dy.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), _ptr(add),
-                                     out.data_ptr(), B, HW, C, groups, float(eps), int(bool(silu)), _dt(x), _stream()), "group_norm_bwd")
+                                     out.data_ptr(), _ptr(ws), B, HW, C, groups, float(eps), int(bool(silu)), _dt(x), _stream()),
+              "group_norm_bwd")
     return out
 
 

@@ -250,9 +250,11 @@ int c2d_legacy_combine(const void* fg, const void* bg, const void* amb, const fl
  * kernel, after c2d_zero_insert2x for the stride-2 convolutions); the entry points below are the pieces without a
  * forward twin.  Same dtype switch as the forward kernels, fp32 accumulation.  `add` (optional, same shape as the
  * output) is summed into the result: the fan-in of residual branches costs no extra pass. */
-/* GroupNorm(+SiLU) adjoint: statistics recomputed from x;  dx = d/dx [act(gn(x))] . dy (+ add) */
-int c2d_group_norm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, int B,
-                       int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
+/* GroupNorm(+SiLU) adjoint: statistics recomputed from x;  dx = d/dx [act(gn(x))] . dy (+ add).
+ * ws (optional): caller-ZEROED scratch of B * C * 32 bytes -- with it the bf16 path runs as three coalesced passes
+ * (channel statistics, adjoint sums, apply) instead of one CTA per (sample, group). */
+int c2d_group_norm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
+                       int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
 /* LayerNorm adjoint over the rows of x[M][C] (+ add) */
 int c2d_layer_norm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, int M, int C, float eps,
                        int dtype, void* stream);

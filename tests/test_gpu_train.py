@@ -100,7 +100,7 @@ def test_conv3x3_data_gradient_through_forward_kernel(stride, up, dtype):
 @pytest.mark.parametrize("B,heads,Nq,Nkv,d,packed", [(2, 8, 256, 256, 40, True), (1, 8, 1024, 1024, 40, True), (2, 8, 64, 64, 160, True),
                                                       (2, 8, 256, 77, 40, False), (2, 8, 100, 77, 80, False), (1, 4, 64, 10, 160, False),
                                                       (2, 8, 1024, 1024, 80, True), (1, 8, 4096, 4096, 40, True), (2, 4, 200, 333, 64, False),
-                                                      (1, 2, 384, 130, 128, False)])
+                                                      (1, 2, 384, 130, 128, False), (2, 8, 256, 256, 160, True), (1, 4, 300, 77, 160, False)])
 def test_attention_bwd(B, heads, Nq, Nkv, d, packed, dtype):
     C = heads * d
     if packed:                       # self-attention: q, k, v are column slices of one [B, N, 3C] buffer
