@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libc2d.so")
+LIB_PATH = os.environ.get("C2D_LIB") or os.path.join(_HERE, "libc2d.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 F32, BF16 = 0, 1

@@ -639,7 +639,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tfull[buf], (it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      constexpr int NCHUNK = GEGLU ? 2 : BN / 32;
+      constexpr int NCHUNK = GEGLU ? BN / 64 : BN / 32;            // GEGLU: 32 outputs per chunk = 32 a + 32 gate columns
       const int c_last = half + 2 * ((NCHUNK - 1 - half) / 2);      // this warp's last chunk
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
@@ -664,14 +664,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
           }
         } else {
+          // accumulator columns: 128-column groups of [a (64) | gate (64)]
+          const int ca = (c >> 1) * 128 + (c & 1) * 32;
           uint32_t ra[32], rg[32];
-          tmem_ld_32x32(t_row + c * 32, ra);
-          tmem_ld_32x32(t_row + 64 + c * 32, rg);
+          tmem_ld_32x32(t_row + ca, ra);
+          tmem_ld_32x32(t_row + ca + 64, rg);
           tmem_ld_wait();
           if (c == c_last) { tc_fence_before(); mbar_arrive(&tempty[buf]); }
           float gg[32];
-          epi_affine32<LNF>(ra, sb + c * 32, scs + c * 32, ln_rstd, -ln_mr, v);
-          epi_affine32<LNF>(rg, sb + 64 + c * 32, scs + 64 + c * 32, ln_rstd, -ln_mr, gg);
+          epi_affine32<LNF>(ra, sb + ca, scs + ca, ln_rstd, -ln_mr, v);
+          epi_affine32<LNF>(rg, sb + ca + 64, scs + ca + 64, ln_rstd, -ln_mr, gg);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) gelu_mul2(v[j], v[j + 1], gg[j], gg[j + 1]);
         }
@@ -1179,6 +1181,20 @@ static int pick_bn(int M, int N) {
   return 64;
 }
 
+// GEGLU projection on the persistent kernel: 128 x 256 tiles.  One N = 256 MMA per k-step costs 162 issue cycles against
+// 2 x 98 for two N = 128 ones, and the A tile is re-streamed from L2 half as often (the K = 320 sites are L2 -> SM bound:
+// knocking out 3 of 4 MMAs did not change their time).  Measured at UNet batch 16 (tools/bench_shapes.py), BN 128 -> 256:
+// 143 -> 128, 113 -> 91, 103 -> 82, 31 -> 26 us for the four levels.  C2D_GEGLU_BN=128 forces the narrow tile (A/B runs).
+static int pick_bn_geglu(int M, int N) {
+  (void)M;
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("C2D_GEGLU_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  return (N % 256 == 0 && forced != 128) ? 256 : 128;
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool linear_tc_supported(const void* x, const void* w, int M, int N, int K, int ldx) {
@@ -1208,7 +1224,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
   int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                 : (geglu ? 128 : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+                 : (geglu ? pick_bn_geglu(M, N) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
   // small M (the low-resolution levels, single-image latency): the wide tile leaves most SMs idle -> 64-column tiles
   if (!pairk && !geglu && !persist && small_bn_enabled() && N % 64 == 0 &&
       ceil_div(M, TC_BM) * ceil_div(N, BN) * 2 <= num_sms())
@@ -1258,7 +1274,10 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
     return launch_tc3<128, 4, false, false>(tmA, tmA2, tmB, p, s);
   }
   const bool lnf = p.ln_stats != nullptr;
-  if (geglu && lnf) return launch_tc2<128, 5, false, true, true>(tmA, tmA2, tmB, p, s);      // folded-LN GEGLU: persistent only
+  if (geglu && lnf) {                                                                         // folded-LN GEGLU: persistent only
+    if (BN == 256) return launch_tc2<256, 3, false, true, true>(tmA, tmA2, tmB, p, s);
+    return launch_tc2<128, 5, false, true, true>(tmA, tmA2, tmB, p, s);
+  }
   if (lnf) {
     if (persist) {
       if (BN == 160) return launch_tc2<160, 5, false, false, true>(tmA, tmA2, tmB, p, s);
@@ -1269,7 +1288,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
     return launch_tc<128, false, false, true>(tmA, tmA2, tmB, p, s);
   }
   if (persist) {
-    if (geglu) return launch_tc2<128, 5, false, true>(tmA, tmA2, tmB, p, s);
+    if (geglu) return BN == 256 ? launch_tc2<256, 3, false, true>(tmA, tmA2, tmB, p, s) : launch_tc2<128, 5, false, true>(tmA, tmA2, tmB, p, s);
     if (BN == 160) return launch_tc2<160, 5, false, false>(tmA, tmA2, tmB, p, s);
     if (BN == 64) return launch_tc2<64, 7, false, false>(tmA, tmA2, tmB, p, s);
     return launch_tc2<128, 5, false, false>(tmA, tmA2, tmB, p, s);
