@@ -1224,7 +1224,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
   int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                 : (geglu ? pick_bn_geglu(M, N) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+                 : (geglu ? (persist ? pick_bn_geglu(M, N) : 128) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
   // small M (the low-resolution levels, single-image latency): the wide tile leaves most SMs idle -> 64-column tiles
   if (!pairk && !geglu && !persist && small_bn_enabled() && N % 64 == 0 &&
       ceil_div(M, TC_BM) * ceil_div(N, BN) * 2 <= num_sms())

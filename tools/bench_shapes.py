@@ -17,11 +17,32 @@ import torch  # noqa: E402
 from clap2diffusion_b200 import ops  # noqa: E402
 
 
+GRAPH = True
+
+
 def timeit(fn, reps):
+    """Average device time of one call in us.  By default the `reps` calls are captured into one CUDA graph and the graph is
+    replayed, so the Python / ctypes / tensor-map-encode cost of a call (~30 us, more than most of these kernels) is not in
+    the number; --no-graph times eager launches."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if GRAPH:
+        st = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(st):
+            fn()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(reps):
+                    fn()
+            g.replay()
+            st.synchronize()
+            e0.record(st)
+            g.replay()
+            e1.record(st)
+            st.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
     e0.record()
     for _ in range(reps):
         fn()
@@ -35,7 +56,10 @@ def main():
     ap.add_argument("--what", default="linear,conv,geglu,attn,gn,ln")
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (includes the host-side cost of a call)")
     a = ap.parse_args()
+    global GRAPH
+    GRAPH = not a.no_graph
     what = set(a.what.split(","))
     dev = torch.device("cuda", 0)
     B = a.batch
