@@ -285,13 +285,13 @@ def run_clap(args):
     pk = peaks()
     fl = n * clap_mod.flops_per_clip()
     print(json.dumps({"metric": "clap_clips_per_sec", "value": n / (ms * 1e-3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16 (log-mel front end fp32)",
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16 (DFT: split-bf16 tcgen05 GEMM, fp32 accumulation; mel / dB in fp32)",
                       "data": "synthetic", "config": {"workload": f"config 4: CLAP HTSAT audio encoder + hierarchical decomposer, "
                                                                    f"{n} synthetic 10 s / 48 kHz clips", "clips": n},
                       "gpu_launches": int(_lib.launch_count() - l0),
                       "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                                    "frac": fl / (ms * 1e-3) / 1e12 / pk["tflops"], "traffic": None,
-                                   "note": "short-K GEMMs (C = 96 .. 768) and an fp32 DFT GEMM: far from the dense-bf16 roof by construction"}}))
+                                   "note": "short-K GEMMs (C = 96 .. 768), HBM-bound at the 4096-token stage, and FFMA window attention: far from the dense-bf16 roof by construction"}}))
 
 
 def run_train(args):

@@ -78,7 +78,8 @@ SIGNATURES = {
     "c2d_norm_scale": [_p, _p, _i, _i, _i, _f, _i, _i, _p],
     "c2d_legacy_combine": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "c2d_stft_frames": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "c2d_power_spectrum": [_p, _p, _ll, _i, _p],
+    "c2d_stft_frames_split": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "c2d_power_spectrum": [_p, _p, _ll, _i, _i, _i, _i, _p],
     "c2d_log_mel_affine": [_p, _p, _p, _p, _ll, _i, _f, _p],
     "c2d_clap_patches": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_window_attention": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],

@@ -29,6 +29,7 @@ import torch
 from . import ops
 
 SR, N_FFT, HOP, N_MEL, N_FRAMES, N_SAMPLES = 48000, 1024, 480, 64, 1001, 480000
+DFT_IM_OFF, DFT_N_PAD = 520, 1040        # tensor-core DFT output row: re at 0..512, im at 520..1032, zero padded to 1040
 SPEC, PATCH, EMBED, WINDOW = 256, 4, 96, 8
 DEPTHS, HEADS = (2, 2, 6, 2), (4, 8, 16, 32)
 HIDDEN, PROJ = 768, 512
@@ -129,6 +130,15 @@ class ClapAudioTower:
         ang = 2.0 * np.pi * np.outer(k, n) / N_FFT
         w["window"] = torch.from_numpy(np.hanning(N_FFT + 1)[:-1].astype(np.float32)).to(dev)
         w["dft"] = torch.from_numpy(np.concatenate([np.cos(ang), np.sin(ang)], 0).astype(np.float32)).to(dev).contiguous()
+        if self.dtype == torch.bfloat16:
+            # tensor-core DFT: constant rows [HI | HI | LO] (bf16 split of the fp32 matrix) against frames [hi | lo | hi];
+            # cos rows at 0..512, sin rows at DFT_IM_OFF..+512, zero rows pad N to a multiple of 16
+            d3 = torch.zeros(DFT_N_PAD, N_FFT, device=dev, dtype=torch.float32)
+            d3[:N_FFT // 2 + 1] = w["dft"][:N_FFT // 2 + 1]
+            d3[DFT_IM_OFF:DFT_IM_OFF + N_FFT // 2 + 1] = w["dft"][N_FFT // 2 + 1:]
+            hi = d3.to(torch.bfloat16)
+            lo = (d3 - hi.float()).to(torch.bfloat16)
+            w["dft3"] = torch.cat([hi, hi, lo], dim=1).contiguous()                  # [1040, 3072]
         w["mel_fb"] = torch.from_numpy(_slaney_mel_filters(self.frequency_min, self.frequency_max).T.astype(np.float32).copy()).to(dev).contiguous()    # [64, 513]
         # eval-mode BatchNorm2d over mel bins folded into the dB kernel: y = dB * a + b
         g, b = self._f32(f"{e}.batch_norm.weight"), self._f32(f"{e}.batch_norm.bias")
@@ -176,9 +186,14 @@ class ClapAudioTower:
         out = torch.empty(B, N_FRAMES, N_MEL, device=self.device, dtype=torch.float32)
         for b0 in range(0, B, self.clip_chunk):
             wv = waves[b0:b0 + self.clip_chunk].contiguous()
-            frames = ops.stft_frames(wv, w["window"], HOP, N_FRAMES)                # [b*1001, 1024]
-            dft = ops.linear(frames, w["dft"])                                      # [b*1001, 1026]  fp32 GEMM
-            power = ops.power_spectrum(dft)                                         # [b*1001, 513]
+            if "dft3" in w:
+                frames3 = ops.stft_frames_split(wv, w["window"], HOP, N_FRAMES)     # [b*1001, 3072] bf16 = [hi | lo | hi]
+                dft = ops.linear(frames3, w["dft3"])                                # [b*1001, 1040] tcgen05, fp32 accumulation
+                power = ops.power_spectrum(dft, nb=N_FFT // 2 + 1, im_off=DFT_IM_OFF)
+            else:
+                frames = ops.stft_frames(wv, w["window"], HOP, N_FRAMES)            # [b*1001, 1024]
+                dft = ops.linear(frames, w["dft"])                                  # [b*1001, 1026]  fp32 GEMM (parity mode)
+                power = ops.power_spectrum(dft)                                     # [b*1001, 513]
             mel = ops.linear(power, w["mel_fb"])                                    # [b*1001, 64]
             ops.log_mel_affine(mel, w["bn_a"], w["bn_b"], 1e-10, out=out[b0:b0 + wv.shape[0]].view(-1, N_MEL))
         return out

@@ -6,6 +6,8 @@
 //   2 x 2 patch-merge gather, token mean, L2 normalisation
 // Reference behaviour: transformers/models/clap/modeling_clap.py (cited per kernel) as called from
 // /root/reference/models/audio_encoder.py:164-174.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace c2d {
@@ -26,13 +28,44 @@ __global__ void stft_frames_kernel(const float* __restrict__ wave, const float* 
   }
 }
 
-// dft[m] = [re(0..nb) | im(0..nb)]  ->  out[m][j] = re^2 + im^2
-__global__ void power_spectrum_kernel(const float* __restrict__ dft, float* __restrict__ out, int nb, long long total) {
+// Split-bf16 framing for the tensor-core DFT (bf16 product mode): x = hi + lo with hi = bf16(x), lo = bf16(x - hi); one row
+// of frames3 is [hi | lo | hi] (3 * n_fft columns) and meets the constant matrix rows [HI | HI | LO], so a single bf16 GEMM
+// with fp32 accumulation yields hi HI + lo HI + hi LO -- the fp32 product up to the dropped lo LO term (2^-18 relative).
+// Plain bf16 operands would put a noise floor 54 dB under each frame's strongest bin, which the log-mel would show.
+__global__ void stft_frames_split_kernel(const float* __restrict__ wave, const float* __restrict__ window, bf16* __restrict__ frames3,
+                                         int T, int n_fft, int hop, int n_frames, long long total8) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int per_row = n_fft >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+    const int k0 = (int)(i % per_row) * 8;
+    const long long row = i / per_row;
+    const int f = (int)(row % n_frames);
+    const long long b = row / n_frames;
+    float hi[8], lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      int t = f * hop + k0 + u - n_fft / 2;
+      if (t < 0) t = -t;
+      if (t >= T) t = 2 * (T - 1) - t;
+      const float x = wave[b * T + t] * window[k0 + u];
+      hi[u] = __bfloat162float(__float2bfloat16_rn(x));
+      lo[u] = x - hi[u];
+    }
+    bf16* dst = frames3 + row * 3 * n_fft + k0;
+    Vec8<bf16>::store(dst, hi);
+    Vec8<bf16>::store(dst + n_fft, lo);
+    Vec8<bf16>::store(dst + 2 * n_fft, hi);
+  }
+}
+
+// dft row m = [re(0..nb) at column 0 | im(0..nb) at column im_off], row pitch ld  ->  out[m][j] = re^2 + im^2
+template <typename T>
+__global__ void power_spectrum_kernel(const T* __restrict__ dft, float* __restrict__ out, int nb, int ld, int im_off, long long total) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int j = (int)(i % nb);
     const long long m = i / nb;
-    const float re = dft[m * 2 * nb + j], im = dft[m * 2 * nb + nb + j];
+    const float re = to_f<T>(dft[m * ld + j]), im = to_f<T>(dft[m * ld + im_off + j]);
     out[i] = fmaf(re, re, im * im);
   }
 }
@@ -146,6 +179,109 @@ window_attention_kernel(const T* __restrict__ qkv, const float* __restrict__ bia
     if (k < d) orow[k] = from_f<T>(o[k]);
 }
 
+// Same operation for head_dim D = 24 (every HTSAT stage: 96/4, 192/8, 384/16, 768/32) or 32, organised for the FMA pipe: the
+// first kernel reads one shared-memory scalar per FMA (LDS-bound at ~1/4 of the FFMA rate).  Here K and V rows sit in shared
+// memory as 16-byte chunks, chunk c of row j at slot (c + j) & 7 (conflict-free row-per-thread fill), and are read back as
+// float4 broadcasts (one LDS.128 per four FMAs).  WA_HPB heads of one window per CTA (thread = query token).
+constexpr int WA_HPB = 2;
+template <typename T, int D>
+__device__ __forceinline__ void wa_load(const T* p, float* f) {
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int c = 0; c < D / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(p + 4 * c);
+      f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) Vec8<T>::load(p + 8 * c, *reinterpret_cast<float(*)[8]>(f + 8 * c));
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(64 * WA_HPB)
+window_attention_d_kernel(const T* __restrict__ qkv, const float* __restrict__ bias, T* __restrict__ out, int H, int W, int C,
+                          int heads, int shift, float scale) {
+  constexpr int WS = 8, NT = 64, NC = D / 4;
+  static_assert(D % 8 == 0 && D <= 32, "window attention: head dim");
+  const int nw = W / WS;
+  const int win = blockIdx.x, hl = threadIdx.x >> 6, head = blockIdx.y * WA_HPB + hl, b = blockIdx.z;
+  const int wy = win / nw, wx = win % nw;
+  const int i = threadIdx.x & 63, iy = i >> 3, ix = i & 7;
+  const int ys = wy * WS + iy, xs = wx * WS + ix;                       // coordinates in the shifted image
+  const int y = (ys + shift) % H, x = (xs + shift) % W;                 // source token
+  const long long tok = (long long)b * H * W + (long long)y * W + x;
+  __shared__ float4 sk[WA_HPB][NT][8], sv[WA_HPB][NT][8];
+  __shared__ int sreg[NT];
+  const T* row = qkv + tok * 3 * C + head * D;
+  float q[D];
+  {
+    float t[D];
+    wa_load<T, D>(row, q);
+#pragma unroll
+    for (int j = 0; j < D; ++j) q[j] *= scale;
+    wa_load<T, D>(row + C, t);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sk[hl][i][(c + i) & 7] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+    wa_load<T, D>(row + 2 * C, t);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sv[hl][i][(c + i) & 7] = make_float4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+  }
+  int reg = 0;
+  if (shift > 0) {
+    const int rh = ys < H - WS ? 0 : (ys < H - shift ? 1 : 2);
+    const int rw = xs < W - WS ? 0 : (xs < W - shift ? 1 : 2);
+    reg = rh * 3 + rw;
+  }
+  if (hl == 0) sreg[i] = reg;
+  __syncthreads();
+  const float4* brow = reinterpret_cast<const float4*>(bias + ((long long)head * NT + i) * NT);
+  float sc[NT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j4 = 0; j4 < NT / 4; ++j4) {
+    const float4 bv = __ldg(brow + j4);
+    const float bj[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j4 * 4 + u;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; c += 2) {
+        const float4 k0 = sk[hl][j][(c + j) & 7], k1 = sk[hl][j][(c + 1 + j) & 7];
+        a0 = fmaf(q[4 * c], k0.x, a0); a0 = fmaf(q[4 * c + 1], k0.y, a0); a0 = fmaf(q[4 * c + 2], k0.z, a0); a0 = fmaf(q[4 * c + 3], k0.w, a0);
+        a1 = fmaf(q[4 * c + 4], k1.x, a1); a1 = fmaf(q[4 * c + 5], k1.y, a1); a1 = fmaf(q[4 * c + 6], k1.z, a1); a1 = fmaf(q[4 * c + 7], k1.w, a1);
+      }
+      float a = (a0 + a1) + bj[u];
+      if (sreg[j] != reg) a += -100.0f;
+      sc[j] = a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.f / sum;
+  float o[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) o[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const float pj = sc[j];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 v = sv[hl][j][(c + j) & 7];
+      o[4 * c] = fmaf(pj, v.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, v.y, o[4 * c + 1]);
+      o[4 * c + 2] = fmaf(pj, v.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, v.w, o[4 * c + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) o[k] *= inv;
+  T* orow = out + tok * C + head * D;
+#pragma unroll
+  for (int c = 0; c < D / 8; ++c) Vec8<T>::store(orow + 8 * c, *reinterpret_cast<const float(*)[8]>(o + 8 * c));
+}
+
 // ClapAudioPatchMerging gather (:712-727): out[b][y2 * W/2 + x2] = cat(x[2y2][2x2], x[2y2+1][2x2], x[2y2][2x2+1], x[2y2+1][2x2+1])
 template <typename T>
 __global__ void patch_merge_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int C, long long total) {
@@ -215,10 +351,23 @@ int c2d_stft_frames(const float* wave, const float* window, float* frames, int B
   return check_launch("stft_frames");
 }
 
-int c2d_power_spectrum(const float* dft, float* out, long long M, int nb, void* stream) {
-  C2D_REQUIRE(dft && out && M > 0 && nb > 0, "power_spectrum: bad args");
+int c2d_stft_frames_split(const float* wave, const float* window, void* frames3, int B, int T, int n_fft, int hop, int n_frames,
+                          void* stream) {
+  C2D_REQUIRE(wave && window && frames3 && B > 0 && T > n_fft / 2 && n_fft > 0 && n_fft % 8 == 0 && hop > 0 && n_frames > 0,
+              "stft_frames_split: bad args");
+  C2D_REQUIRE((n_frames - 1) * hop + n_fft / 2 < 2 * T - 1, "stft_frames_split: frames run past the reflect padding");
+  C2D_REQUIRE((reinterpret_cast<uintptr_t>(frames3) & 15) == 0, "stft_frames_split: output must be 16-byte aligned");
+  const long long total8 = (long long)B * n_frames * (n_fft / 8);
+  stft_frames_split_kernel<<<ew_grid2(total8, 256), 256, 0, (cudaStream_t)stream>>>(wave, window, (bf16*)frames3, T, n_fft, hop,
+                                                                                   n_frames, total8);
+  return check_launch("stft_frames_split");
+}
+
+int c2d_power_spectrum(const void* dft, float* out, long long M, int nb, int ld, int im_off, int dtype, void* stream) {
+  C2D_REQUIRE(dft && out && M > 0 && nb > 0 && im_off >= nb && ld >= im_off + nb, "power_spectrum: bad args");
   const long long total = M * nb;
-  power_spectrum_kernel<<<ew_grid2(total, 256), 256, 0, (cudaStream_t)stream>>>(dft, out, nb, total);
+  CLAP_DISPATCH_T(dtype, power_spectrum_kernel<T><<<ew_grid2(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)dft, out, nb, ld,
+                                                                                                        im_off, total);)
   return check_launch("power_spectrum");
 }
 
@@ -244,6 +393,24 @@ int c2d_window_attention(const void* qkv, const float* bias, void* out, int B, i
   C2D_REQUIRE(H % 8 == 0 && W % 8 == 0, "window_attention: H=%d, W=%d must be multiples of the 8 x 8 window", H, W);
   C2D_REQUIRE(C % heads == 0 && C / heads <= 32, "window_attention: head_dim %d > 32", C / heads);
   C2D_REQUIRE(shift >= 0 && shift < 8, "window_attention: bad shift %d", shift);
+  static int fast = -1;                 // C2D_WINATTN=0: first-generation kernel (A/B runs)
+  if (fast < 0) {
+    const char* e = getenv("C2D_WINATTN");
+    fast = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int d = C / heads;
+  if (fast && (d == 24 || d == 32) && heads % WA_HPB == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
+    dim3 gridd((H / 8) * (W / 8), heads / WA_HPB, B);
+    if (d == 24) {
+      CLAP_DISPATCH_T(dtype, window_attention_d_kernel<T, 24><<<gridd, 64 * WA_HPB, 0, (cudaStream_t)stream>>>(
+                                 (const T*)qkv, bias, (T*)out, H, W, C, heads, shift, scale);)
+    } else {
+      CLAP_DISPATCH_T(dtype, window_attention_d_kernel<T, 32><<<gridd, 64 * WA_HPB, 0, (cudaStream_t)stream>>>(
+                                 (const T*)qkv, bias, (T*)out, H, W, C, heads, shift, scale);)
+    }
+    return check_launch("window_attention");
+  }
   dim3 grid((H / 8) * (W / 8), heads, B);
   CLAP_DISPATCH_T(dtype, window_attention_kernel<T><<<grid, 64, 0, (cudaStream_t)stream>>>((const T*)qkv, bias, (T*)out, H, W, C,
                                                                                        heads, shift, scale);)

@@ -686,14 +686,35 @@ def stft_frames(wave, window, hop: int, n_frames: int, *, out=None):
     return out
 
 
-def power_spectrum(dft, *, out=None):
-    """dft fp32 [M, 2*nb] = [re | im] -> fp32 [M, nb]."""
-    _dev(dft)
-    M, nb2 = dft.shape
-    assert dft.is_contiguous() and nb2 % 2 == 0
+def stft_frames_split(wave, window, hop: int, n_frames: int, *, out=None):
+    """wave fp32 [B,T], window fp32 [n_fft] -> bf16 [B*n_frames, 3*n_fft] = [hi | lo | hi] (split-bf16 operand of the
+    tensor-core DFT: meets constant-matrix rows [HI | HI | LO])."""
+    _dev(wave)
+    B, T = wave.shape
+    n_fft = window.numel()
+    assert wave.is_contiguous() and window.is_contiguous()
     if out is None:
-        out = torch.empty(M, nb2 // 2, device=dft.device, dtype=torch.float32)
-    check(lib.c2d_power_spectrum(_f32(dft, "dft").data_ptr(), out.data_ptr(), M, nb2 // 2, _stream()), "power_spectrum")
+        out = torch.empty(B * n_frames, 3 * n_fft, device=wave.device, dtype=torch.bfloat16)
+    check(lib.c2d_stft_frames_split(_f32(wave, "wave").data_ptr(), _f32(window, "window").data_ptr(), out.data_ptr(), B, T, n_fft,
+                                    int(hop), int(n_frames), _stream()), "stft_frames_split")
+    return out
+
+
+def power_spectrum(dft, *, nb: Optional[int] = None, im_off: Optional[int] = None, out=None):
+    """dft [M, ld] (fp32 or bf16) with re(0..nb) at column 0 and im(0..nb) at column im_off -> fp32 [M, nb] = re^2 + im^2.
+    Default layout: ld = 2*nb, im_off = nb."""
+    _dev(dft)
+    M, ld = dft.shape
+    if nb is None:
+        assert ld % 2 == 0
+        nb = ld // 2
+    if im_off is None:
+        im_off = nb
+    assert dft.is_contiguous() and ld >= im_off + nb
+    if out is None:
+        out = torch.empty(M, nb, device=dft.device, dtype=torch.float32)
+    check(lib.c2d_power_spectrum(dft.data_ptr(), out.data_ptr(), M, int(nb), int(ld), int(im_off), _dt(dft), _stream()),
+          "power_spectrum")
     return out
 
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 5   /* 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
+#define C2D_ABI_VERSION 6   /* 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
                              * 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
                              *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
@@ -305,8 +305,14 @@ int c2d_pack_geglu(const float* w, const float* bias, void* w_out, float* bias_o
 /* frames[(b*n_frames+f)][k] = wave[b][reflect(f*hop + k - n_fft/2)] * window[k]  (centered STFT framing, fp32) */
 int c2d_stft_frames(const float* wave, const float* window, float* frames, int B, int T, int n_fft, int hop, int n_frames,
                     void* stream);
-/* dft [M][2*nb] = [re | im] (the fp32 GEMM of the frames against the constant DFT matrix) -> out [M][nb] = re^2 + im^2 */
-int c2d_power_spectrum(const float* dft, float* out, long long M, int nb, void* stream);
+/* bf16 product mode: frames3 [B*n_frames][3*n_fft] bf16 = [hi | lo | hi] with x = hi + lo (hi = bf16(x), lo = bf16(x - hi)).
+ * Against constant-matrix rows [HI | HI | LO] one bf16 tensor-core GEMM (c2d_linear, fp32 accumulation) gives
+ * hi HI + lo HI + hi LO: the DFT at ~2^-16 operand precision instead of an fp32 FFMA GEMM.  n_fft % 8 == 0. */
+int c2d_stft_frames_split(const float* wave, const float* window, void* frames3, int B, int T, int n_fft, int hop, int n_frames,
+                          void* stream);
+/* dft row m = [re(0..nb) at column 0 | im(0..nb) at column im_off], row pitch ld elements of `dtype` (the GEMM of the frames
+ * against the constant DFT matrix) -> out fp32 [M][nb] = re^2 + im^2 */
+int c2d_power_spectrum(const void* dft, float* out, long long M, int nb, int ld, int im_off, int dtype, void* stream);
 /* y = 10 log10(max(x, floor)) * a[f] + b[f]: power_to_db fused with the eval-mode BatchNorm2d over mel bins */
 int c2d_log_mel_affine(const float* x, const float* a, const float* b, float* y, long long M, int F, float floor_value,
                        void* stream);

@@ -47,7 +47,7 @@ def test_front_end_kernels():
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("B,H,C,heads,shift", [(2, 64, 96, 4, 0), (2, 64, 96, 4, 4), (3, 32, 192, 8, 4), (2, 16, 384, 16, 4),
-                                               (5, 8, 768, 32, 0)])
+                                               (5, 8, 768, 32, 0), (2, 16, 128, 4, 4), (1, 16, 80, 4, 0)])
 def test_window_attention(B, H, C, heads, shift, dtype, tol):
     qkv = rnd(B, H * H, 3 * C, seed=1).to(dtype)
     bias = rnd(heads, 64, 64, seed=2, scale=0.5)
@@ -101,6 +101,27 @@ def test_clap_encoder_bf16_vs_hf_golden(clap_setup):
     # batch invariance: a clip's embedding does not depend on its batch neighbours (data-parallel sharding by clip)
     one = tower.encode(waves[1:2])
     assert rel(one, emb[1:2]) < 1e-2
+
+
+def test_bf16_mode_log_mel_on_tensor_cores(clap_setup):
+    """Product mode computes the 1024-point DFT as ONE split-bf16 tcgen05 GEMM ([hi | lo | hi] x [HI | HI | LO]); the
+    log-mel (dB scale) stays within 2e-3 relative L2 of the Hugging Face features (bf16 rounding of re / im: <= 0.035 dB)
+    -- plain bf16 operands would put a noise floor 54 dB under each frame's peak."""
+    g, sd, waves = clap_setup
+    tower = ClapAudioTower(sd, device=DEV, dtype=torch.bfloat16)
+    assert "dft3" in tower.w and tuple(tower.w["dft3"].shape) == (1040, 3072)
+    n0 = ops._lib.launch_count()
+    mel = (tower.log_mel(waves) - tower.w["bn_b"]) / tower.w["bn_a"]
+    assert ops._lib.launch_count() > n0
+    ref = torch.from_numpy(g["mel"][:, 0])
+    e = rel(mel, ref)
+    worst = float((mel.cpu() - ref).abs().max())
+    print("bf16-mode log-mel: rel-L2 %.1e, worst bin %.3f dB" % (e, worst))
+    assert e < 2e-3 and worst < 0.5
+    # the split: hi + lo reproduces the fp32 frames to ~2^-17
+    f32 = ops.stft_frames(waves[:1].contiguous(), tower.w["window"], 480, 1001)
+    f3 = ops.stft_frames_split(waves[:1].contiguous(), tower.w["window"], 480, 1001)
+    assert torch.equal(f3[:, :1024], f3[:, 2048:]) and rel(f3[:, :1024].float() + f3[:, 1024:2048].float(), f32) < 2e-5
 
 
 def test_drop_in_audio_encoder(clap_setup):

@@ -337,9 +337,18 @@ def stft_frames(wave, window, hop, n_frames, *, out=None):
     return (w[:, idx] * window[None, None, :]).reshape(-1, n_fft).contiguous()
 
 
-def power_spectrum(dft, *, out=None):
-    nb = dft.shape[1] // 2
-    return dft[:, :nb] ** 2 + dft[:, nb:] ** 2
+def stft_frames_split(wave, window, hop, n_frames, *, out=None):
+    x = stft_frames(wave, window, hop, n_frames)
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi], dim=1).contiguous()
+
+
+def power_spectrum(dft, *, nb=None, im_off=None, out=None):
+    nb = dft.shape[1] // 2 if nb is None else nb
+    im_off = nb if im_off is None else im_off
+    d = dft.float()
+    return d[:, :nb] ** 2 + d[:, im_off:im_off + nb] ** 2
 
 
 def log_mel_affine(x, a, b, floor=1e-10, *, out=None):
