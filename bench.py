@@ -256,7 +256,7 @@ def run_clap(args):
     """`--clap`: BASELINE config 4 -- CLAP HTSAT audio encoder + hierarchical decomposer forward on a batch of synthetic
     10 s clips (default 256), waveforms resident on the device; prints one JSON line (clips/s)."""
     import contextlib
-    from clap2diffusion_b200 import _lib, clap as clap_mod, synthetic
+    from clap2diffusion_b200 import _lib, clap as clap_mod, ops, synthetic
     from clap2diffusion_b200.models.audio_encoder import CLAPAudioEncoder
     from clap2diffusion_b200.models.hierarchical_audio_v4 import ImprovedHierarchicalAudioEncoder
     dev = torch.device("cuda", 0)
@@ -268,8 +268,8 @@ def run_clap(args):
     waves = torch.from_numpy(np.concatenate([base] * ((n + 7) // 8))[:n]).to(dev)
 
     def step():
-        emb = enc.encode_audio(waves)
-        return hier.encode(emb, with_tokens77=True)
+        emb = enc.encode_audio(waves)                                   # fp32 [n, 512], unit norm
+        return hier.encode(ops.cast(emb, torch.bfloat16), with_tokens77=True)   # product mode: decomposer / projector GEMMs on tcgen05
 
     for _ in range(max(args.warmup, 1)):
         step()

@@ -26,7 +26,7 @@ def main():
     waves = torch.from_numpy(np.concatenate([base] * ((n + 7) // 8))[:n]).to(dev)
 
     def step():
-        return hier.encode(enc.encode_audio(waves), with_tokens77=True)
+        return hier.encode(ops.cast(enc.encode_audio(waves), torch.bfloat16), with_tokens77=True)
 
     for _ in range(2):
         step()
