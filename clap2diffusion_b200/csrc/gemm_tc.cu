@@ -116,6 +116,26 @@ __device__ __forceinline__ void ln_row_coeffs(const TcParams& p, int m, float& r
   ln_row_finish(p, ln_row_load(p, m), rstd, mr);
 }
 
+// activation of 32 staged values: the switch is hoisted out of the element loop and GELU runs on the packed f32x2 form
+// (the fc1 layers of the CLAP tower have K = 96 .. 768: their epilogue is the kernel)
+__device__ __forceinline__ void epi_act32(float (&v)[32], int act) {
+  if (act == C2D_ACT_NONE) return;
+  if (act == C2D_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float a = 1.f, b = 1.f;
+      gelu_mul2(a, b, v[j], v[j + 1]);
+      v[j] = a; v[j + 1] = b;
+    }
+  } else if (act == C2D_ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+
 constexpr float STATS_SCALE = 1048576.0f;      // 2^20
 
 // Epilogue helper.  Every lane holds sums (s) and sums of squares (q) of its 8 columns over the rows it drained;
@@ -362,10 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (n + j < p.N) v[j] += __ldg(rv + n + j);
           }
-          if (p.act != C2D_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-          }
+          epi_act32(v, p.act);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(srow + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
@@ -659,10 +676,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int j = 0; j < 32; ++j) if (n0 + c * 32 + j < p.N) v[j] += __ldg(rv + j);
             }
           }
-          if (p.act != C2D_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-          }
+          epi_act32(v, p.act);
         } else {
           // accumulator columns: 128-column groups of [a (64) | gate (64)]
           const int ca = (c >> 1) * 128 + (c & 1) * 32;
@@ -949,10 +963,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 32; ++j) if (n0 + c * 32 + j < p.N) v[j] += __ldg(rv + j);
           }
         }
-        if (p.act != C2D_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act_fast(v[j], p.act);
-        }
+        epi_act32(v, p.act);
       } else {
         // accumulator columns: 128-column groups of [a (64) | gate (64)]; output chunk c covers 32 outputs
         const int grp = c >> 1, sub = c & 1;
@@ -1174,9 +1185,17 @@ static bool small_bn_enabled() {
 }
 
 // tile width: widest tile that still yields at least one tile per SM, else 64 (more CTAs, deeper ring)
+// 160 or 128 columns.  A 160-column tile drains as 5 chunks over 2 warp halves (3 + 2) against 4 (2 + 2): when the epilogue
+// bounds the kernel (K <= 768) it costs 3 units per tile against 2, so it is chosen when it divides N (UNet widths) or when it
+// saves a third of the tiles (N = 288: 2 tiles instead of 3; measured 419 -> 349 us at M = 2^20, K = 96, while N = 1152 went
+// 89 -> 110 us on 8 x 160 instead of 9 x 128)
+static int wide_bn(int N) {
+  if (N % 160 == 0) return 160;
+  return 3 * ceil_div(N, 160) <= 2 * ceil_div(N, 128) ? 160 : 128;
+}
 static int pick_bn(int M, int N) {
   const int mt = ceil_div(M, TC_BM);
-  const int wide = (N % 160 == 0) ? 160 : 128;
+  const int wide = wide_bn(N);
   if (mt * ceil_div(N, wide) >= num_sms() || N <= 64) return wide;
   return 64;
 }
@@ -1224,7 +1243,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
   int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
-                 : (geglu ? (persist ? pick_bn_geglu(M, N) : 128) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : ((N % 160 == 0) ? 160 : 128)));
+                 : (geglu ? (persist ? pick_bn_geglu(M, N) : 128) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : wide_bn(N)));
   // small M (the low-resolution levels, single-image latency): the wide tile leaves most SMs idle -> 64-column tiles
   if (!pairk && !geglu && !persist && small_bn_enabled() && N % 64 == 0 &&
       ceil_div(M, TC_BM) * ceil_div(N, BN) * 2 <= num_sms())

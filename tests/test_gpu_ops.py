@@ -262,7 +262,7 @@ def test_group_norm_two_source(dtype):
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("M,C", [(8192, 320), (300, 1280), (77, 768), (5, 6), (33, 192)])
+@pytest.mark.parametrize("M,C", [(8192, 320), (300, 1280), (77, 768), (5, 6), (33, 192), (4099, 96), (1000, 64), (37, 24), (513, 128)])
 def test_layer_norm(M, C, dtype):
     x = rnd(M, C, dtype=dtype) * 3 + 1
     g, b = 1 + 0.1 * rnd(C, seed=1), 0.1 * rnd(C, seed=2)
