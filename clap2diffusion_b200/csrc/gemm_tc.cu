@@ -454,8 +454,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(v[j]);
           }
+          if (p.stats) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+            for (int j = 0; j < 8; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+          }
           if (p.rowstats_out) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -735,7 +737,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
           }
-          if (!GEGLU) {                 // the GEGLU projection never feeds a GroupNorm: no channel statistics
+          if (!GEGLU && p.stats) {      // the GEGLU projection never feeds a GroupNorm: no channel statistics
 #pragma unroll
             for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
           }
@@ -1029,8 +1031,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 8; ++j) if (j < nvalid) yp[j] = __float2bfloat16_rn(o[j]);
         }
+        if (p.stats) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+          for (int j = 0; j < 8; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
+        }
       }
       if (p.stats && mrow0 < p.M) {
         const int bimg = mrow0 / p.stats_rows;
