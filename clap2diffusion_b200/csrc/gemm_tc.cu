@@ -116,6 +116,34 @@ __device__ __forceinline__ void ln_row_coeffs(const TcParams& p, int m, float& r
   ln_row_finish(p, ln_row_load(p, m), rstd, mr);
 }
 
+// Drain of one staged 32-row x 32-column chunk for the common case -- interior rows (all 32 valid), 16-byte aligned y
+// (and residual), no statistics of any kind: lane = (row rsub of an 8-row block, 8-column group g), four 16-byte stores
+// per lane, the four residual loads issued first.  The general loop below spends ~6 index / predicate / branch
+// instructions per useful one (ncu on M = 2^20, N = 288, K = 96: 445 warp instructions per chunk, 70 of them data
+// movement or arithmetic), which bounds every GEMM whose main loop is short (K <= 384: the CLAP tower, the UNet's
+// 64 x 64-level projections).  `srow0` = this lane's first staged row at its column group, `ncol_ok` = the group lies in N.
+__device__ __forceinline__ void drain32_fast(const float* srow0, int pitch, bf16* yp, long long ldy, const bf16* rp, long long ldr,
+                                             bool ncol_ok) {
+  if (!ncol_ok) return;
+  uint4 res[4];
+  if (rp) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) res[u] = *reinterpret_cast<const uint4*>(rp + (long long)u * 8 * ldr);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float* sp = srow0 + (size_t)u * 8 * pitch;
+    const float4 f0 = *reinterpret_cast<const float4*>(sp), f1 = *reinterpret_cast<const float4*>(sp + 4);
+    float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    if (rp) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    }
+    Vec8<bf16>::store(yp + (long long)u * 8 * ldy, v);
+  }
+}
+
 // activation of 32 staged values: the switch is hoisted out of the element loop and GELU runs on the packed f32x2 form
 // (the fc1 layers of the CLAP tower have K = 96 .. 768: their epilogue is the kernel)
 __device__ __forceinline__ void epi_act32(float (&v)[32], int act) {
@@ -415,6 +443,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rsub = lane >> 2, g = lane & 3;
       const int mrow0 = m0 + q * 32;
       float rsum[4] = {0.f, 0.f, 0.f, 0.f}, rsq[4] = {0.f, 0.f, 0.f, 0.f};      // per-row partials (rowstats_out)
+      const bool fast = !p.stats && !p.rowstats_out && vec_y && (!p.residual || vec_r) && (ncols % 8 == 0) && m0 + TC_BM <= p.M;
+      if (fast) {
+        const long long row = mrow0 + rsub;
+#pragma unroll 1
+        for (int c = half; c < NOUT / 32; c += 2) {
+          const int n = nbase + c * 32 + g * 8;
+          drain32_fast(stage + (size_t)rsub * PITCH + c * 32 + g * 8, PITCH, p.y + row * p.ldy + n, p.ldy,
+                       p.residual ? p.residual + row * p.ldr + n : nullptr, p.ldr, n < ncols);
+        }
+      } else
 #pragma unroll 1
       for (int c = half; c < NOUT / 32; c += 2) {
         const int n = nbase + c * 32 + g * 8;
@@ -703,6 +741,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int mrow0 = m0 + q * 32;
         const int n = nbase + c * 32 + g * 8;
         const int nvalid = ncols - n;
+        if ((GEGLU || !p.stats) && vec_y && (!p.residual || vec_r) && (ncols % 8 == 0) && m0 + TC_BM <= p.M) {
+          const long long row = mrow0 + rsub;
+          drain32_fast(stage + (size_t)rsub * Cfg::EPI_PITCH + g * 8, Cfg::EPI_PITCH, p.y + row * p.ldy + n, p.ldy,
+                       p.residual ? p.residual + row * p.ldr + n : nullptr, p.ldr, n < ncols);
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int m = mrow0 + u * 8 + rsub;
