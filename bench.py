@@ -291,7 +291,7 @@ def run_clap(args):
                       "gpu_launches": int(_lib.launch_count() - l0),
                       "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                                    "frac": fl / (ms * 1e-3) / 1e12 / pk["tflops"], "traffic": None,
-                                   "note": "short-K GEMMs (C = 96 .. 768), HBM-bound at the 4096-token stage, and FFMA window attention: far from the dense-bf16 roof by construction"}}))
+                                   "note": "short-K GEMMs (C = 96 .. 768), HBM / epilogue-bound at the 4096-token stage, and 64-token window attention: far from the dense-bf16 roof by construction"}}))
 
 
 def run_train(args):

@@ -340,6 +340,13 @@ using namespace c2d;
   else if ((dtype) == C2D_BF16) { using T = bf16; __VA_ARGS__ }  \
   else { set_error("bad dtype %d", (int)(dtype)); return C2D_ERR_ARG; }
 
+namespace c2d {
+// clap_attn_tc.cu: tcgen05 kernel (bf16, head dim 24 | 32)
+bool window_attention_tc_supported(const void* qkv, const float* bias, const void* out, int C, int heads);
+int window_attention_tc(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads, int shift, float scale,
+                        cudaStream_t s);
+}  // namespace c2d
+
 extern "C" {
 
 int c2d_stft_frames(const float* wave, const float* window, float* frames, int B, int T, int n_fft, int hop, int n_frames,
@@ -393,11 +400,13 @@ int c2d_window_attention(const void* qkv, const float* bias, void* out, int B, i
   C2D_REQUIRE(H % 8 == 0 && W % 8 == 0, "window_attention: H=%d, W=%d must be multiples of the 8 x 8 window", H, W);
   C2D_REQUIRE(C % heads == 0 && C / heads <= 32, "window_attention: head_dim %d > 32", C / heads);
   C2D_REQUIRE(shift >= 0 && shift < 8, "window_attention: bad shift %d", shift);
-  static int fast = -1;                 // C2D_WINATTN=0: first-generation kernel (A/B runs)
+  static int fast = -1;                 // C2D_WINATTN=0: first-generation kernel, 1: float4-broadcast FFMA kernel (A/B runs)
   if (fast < 0) {
     const char* e = getenv("C2D_WINATTN");
-    fast = (e && e[0] == '0') ? 0 : 1;
+    fast = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
   }
+  if (fast == 2 && dtype == C2D_BF16 && window_attention_tc_supported(qkv, bias, out, C, heads))
+    return window_attention_tc(qkv, bias, out, B, H, W, C, heads, shift, scale, (cudaStream_t)stream);
   const int d = C / heads;
   if (fast && (d == 24 || d == 32) && heads % WA_HPB == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) {
