@@ -285,12 +285,14 @@ class FrozenUNetGrad:
 
 class Stage3Trainer:
     """``Stage3Trainer(unet_sd, hier, proc_sd).train_step(batch)``: one optimiser step of the audio attention processors
-    through the frozen UNet.  One instance per GPU; ``group`` (optional) is the data-parallel process group."""
+    through the frozen UNet.  One instance per GPU; ``group`` (optional) is the data-parallel process group (default: the
+    world group when ``torch.distributed`` is initialised; ``data_parallel=False`` opts out)."""
 
     def __init__(self, unet_sd: Dict[str, torch.Tensor], hier, proc_sd: Optional[Dict[str, Dict[str, torch.Tensor]]] = None,
                  device="cuda", dtype=torch.bfloat16, mode: str = "add", learning_rate: float = 1e-5,
                  weight_decay: float = 0.01, num_steps: int = 3000, eta_min: float = 1e-6, gradient_clipping: float = 0.5,
-                 betas=(0.9, 0.999), adam_eps: float = 1e-8, group=None, diffusion_weight: float = 2.0):
+                 betas=(0.9, 0.999), adam_eps: float = 1e-8, group=None, diffusion_weight: float = 2.0,
+                 data_parallel: bool = True):
         if mode != "add":
             raise ValueError("the training step differentiates the 'add' injection (the reference's default mode)")
         self.device, self.dtype = torch.device(device), dtype
@@ -339,7 +341,8 @@ class Stage3Trainer:
         self.diffusion_weight = diffusion_weight
         self.group = group
         self.world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        # data_parallel=False: a stand-alone replica inside an initialised process group (no broadcast, no all-reduce)
+        if data_parallel and (group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(group)
         if self.world > 1:
             # DDP semantics: every replica starts from rank 0's parameters (the processors' tensors are views of `flat`)

@@ -30,11 +30,11 @@ def _worker(rank, world, port, q):
     full = make_batch(B=2, h=8, w=8, seed=5)
     mine = {k: v[rank:rank + 1] for k, v in full.items()}
 
-    def trainer():
+    def trainer(**kw):
         hier = ImprovedHierarchicalAudioEncoder().eval()
         hier.load_state_dict(W["hier"])
         return Stage3Trainer(W["unet"], hier, {l: W[f"proc_{l}"] for l in LEVELS}, device="cpu", dtype=torch.float32,
-                             learning_rate=1e-3, num_steps=10)
+                             learning_rate=1e-3, num_steps=10, **kw)
     with torch_ops.installed(), torch.no_grad():
         tr = trainer()
         assert tr.world == world
@@ -44,8 +44,8 @@ def _worker(rank, world, port, q):
         out = {"grad": g.numpy(), "flat": tr.flat.clone().numpy(), "loss": float(loss)}
         if rank == 0:          # single-process reference on the full batch
             dist_world = tr.world
-            ref = trainer()
-            ref.world, ref.group = 1, None
+            ref = trainer(data_parallel=False)         # no collectives: rank 1 does not build one
+            assert ref.world == 1
             ref_loss = ref.forward_backward(full["audio_embedding"], full["image_latents"], full["text_embedding"], full["noise"], full["timesteps"])
             out["ref_grad"] = ref.grad.clone().numpy()
             ref.optimizer_step()
