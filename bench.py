@@ -335,6 +335,8 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if not args.no_train_graph:
+        tr.capture(batches[0])               # the whole step (forward, reverse pass, all-reduce buckets, update) as ONE CUDA graph
     for i in range(max(args.warmup, 1)):
         tr.train_step(batches[i % 4])
     barrier()
@@ -364,7 +366,8 @@ def run_train(args):
                           "config": {"workload": f"config 5: stage-3 fine-tune step, audio attention processors trainable (297,411 parameters), "
                                                  f"SD-1.5 UNet frozen, {b} samples/GPU (global batch {world * b}), 64x64 latents, DDP over {world} GPU(s)",
                                      "per_gpu_batch": b},
-                          "gpu_launches": int(_lib.launch_count() - l0), "replicas_identical": same,
+                          "gpu_launches": int(_lib.launch_count() - l0) if args.no_train_graph else tr.graph_launches * args.steps,
+                          "cuda_graph": not args.no_train_graph, "replicas_identical": same,
                           "loss": float(out["diffusion"]) * world, "grad_norm": float(out["grad_norm"])}))
     if world > 1:
         dist.destroy_process_group()
@@ -610,6 +613,7 @@ def main():
     ap.add_argument("--ncu-step", action="store_true", help="profile one eager UNet step (for ncu --profile-from-start off)")
     ap.add_argument("--train", action="store_true", help="config 5: stage-3 fine-tune step throughput (samples/s)")
     ap.add_argument("--train-batch", type=int, default=4, help="with --train: samples per GPU (4 x 8 GPUs = global batch 32)")
+    ap.add_argument("--no-train-graph", action="store_true", help="with --train: eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
     if args.train:
         run_train(args)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "c2d_sumsq": [_p, _ll, _p, _p],
     "c2d_clip_scale": [_p, _f, _p, _p, _p],
     "c2d_adamw_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _p, _p],
+    "c2d_adamw_step_sched": [_p, _p, _p, _p, _ll, _p, _i, _p, _f, _f, _f, _f, _p, _p],
     "c2d_pack_conv3x3": [_p, _p, _i, _i, _i, _p],
     "c2d_pack_geglu": [_p, _p, _p, _p, _i, _i, _i, _p],
 }

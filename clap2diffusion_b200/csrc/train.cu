@@ -290,6 +290,27 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// The same update with the schedule on the device: sched[t] = (learning rate, 1 - beta1^(t+1), 1 - beta2^(t+1)) for optimiser step
+// t, *step_dev = number of steps taken so far.  Nothing about the step is a kernel argument, so the launch can sit in a CUDA
+// graph that is replayed for every step (the caller increments *step_dev after the launch, inside the same graph).
+__global__ void adamw_sched_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                   long long n, const float* __restrict__ sched, int sched_len, const int* __restrict__ step_dev,
+                                   float b1, float b2, float eps, float wd, const float* __restrict__ grad_scale) {
+  int t = *step_dev;
+  t = t < 0 ? 0 : (t >= sched_len ? sched_len - 1 : t);
+  const float lr = sched[3 * t], bc1 = sched[3 * t + 1], bc2 = sched[3 * t + 2];
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ attention backward
 // Recompute-form flash attention backward on the FFMA pipe (fp32 accumulation; fp32 or bf16 storage).
 //   S = scale Q K^T, P = softmax(S), O = P V;  D_i = <dO_i, O_i>;  dV = P^T dO;  dP = dO V^T;  dS = P o (dP - D);
@@ -741,6 +762,15 @@ int c2d_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<tr_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                    weight_decay, bc1, bc2, grad_scale);
+  return check_launch("adamw_step");
+}
+
+int c2d_adamw_step_sched(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* sched,
+                         int sched_len, const int* step_dev, float beta1, float beta2, float eps, float weight_decay,
+                         const float* grad_scale, void* stream) {
+  C2D_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && sched && sched_len > 0 && step_dev, "adamw_step_sched: bad args");
+  adamw_sched_kernel<<<tr_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, sched, sched_len, step_dev,
+                                                                         beta1, beta2, eps, weight_decay, grad_scale);
   return check_launch("adamw_step");
 }
 

@@ -944,6 +944,20 @@ def clip_scale(sumsq_acc, max_norm: float, scale_out, norm_out=None):
     return scale_out
 
 
+def adamw_step_sched(param, grad, exp_avg, exp_avg_sq, sched, step_dev, beta1, beta2, eps, weight_decay, grad_scale=None):
+    """AdamW with the schedule on the device: sched fp32 [T, 3] = (lr, 1 - beta1^(t+1), 1 - beta2^(t+1)), step_dev int32 [1] = steps
+    taken so far (the caller increments it).  No per-step kernel argument: the launch can be replayed from a CUDA graph."""
+    _dev(param)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    assert sched.dtype == torch.float32 and sched.is_contiguous() and sched.dim() == 2 and sched.shape[1] == 3
+    assert step_dev.dtype == torch.int32 and step_dev.numel() == 1
+    check(lib.c2d_adamw_step_sched(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), param.numel(),
+                                   sched.data_ptr(), sched.shape[0], step_dev.data_ptr(), float(beta1), float(beta2), float(eps),
+                                   float(weight_decay), _ptr(grad_scale), _stream()), "adamw_step_sched")
+    return param
+
+
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step: int, grad_scale=None):
     _dev(param)
     for t in (param, grad, exp_avg, exp_avg_sq):

@@ -349,6 +349,14 @@ class Stage3Trainer:
             torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(group, 0) if group is not None else 0, group=group)
         self._time_table: Optional[torch.Tensor] = None      # [1000, sum(Cout)] rows of SD15UNet.time_table, built on first use
         self.step_count = 0
+        # the optimiser's schedule lives on the device (row t: learning rate and the two bias corrections of step t) next to a
+        # device step counter, so that a training step has no host-side scalar and can be replayed from ONE CUDA graph
+        tt = range(num_steps + 1)
+        self._sched = torch.tensor([[self.lr(t), 1.0 - betas[0] ** (t + 1), 1.0 - betas[1] ** (t + 1)] for t in tt],
+                                   dtype=torch.float64).to(torch.float32).to(self.device).contiguous()
+        self._step_dev = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self._graph = None
+        self._static: Dict[str, torch.Tensor] = {}
         self._scalars = torch.zeros(4, device=self.device, dtype=torch.float32)       # [clip scale, grad norm, -, -]
         self._acc = torch.zeros(2, device=self.device, dtype=torch.float64)           # [loss, sum of squares]
 
@@ -449,8 +457,9 @@ class Stage3Trainer:
         self.step_count += 1
         ops.sumsq(self.grad, self._acc[1:2])
         ops.clip_scale(self._acc[1:2], self.clip, self._scalars[0:1], self._scalars[1:2])
-        ops.adamw_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr(self.step_count - 1), self.betas[0],
-                       self.betas[1], self.adam_eps, self.wd, self.step_count, self._scalars[0:1])
+        ops.adamw_step_sched(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self._sched, self._step_dev, self.betas[0],
+                             self.betas[1], self.adam_eps, self.wd, self._scalars[0:1])
+        self._step_dev.add_(1)
         for p in self.procs.values():          # parameters changed under the processors' cast caches
             p._cache._c.clear()
             p._kv_cache.clear()
@@ -459,10 +468,56 @@ class Stage3Trainer:
         """batch: audio_embedding [B,512], image_latents [B,4,H,W], text_embedding [B,77,768] (reference :134-136) plus
         the step's randomness noise [B,4,H,W] and timesteps [B] (drawn by the caller so that runs are reproducible).
         Returns device tensors {'diffusion': loss (this rank's share of the mean), 'grad_norm': pre-clip global norm}."""
+        if self._graph is not None:
+            return self._replay(batch)
         loss = self.forward_backward(batch["audio_embedding"], batch["image_latents"], batch["text_embedding"],
                                      batch["noise"], batch["timesteps"])
         self.optimizer_step()
         return {"diffusion": loss.clone(), "grad_norm": self._scalars[1:2].clone()}
+
+    # ---------------------------------------------------------------- the step as one CUDA graph
+    _KEYS = ("audio_embedding", "image_latents", "text_embedding", "noise", "timesteps")
+
+    def capture(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Capture forward + reverse pass + all-reduce buckets + optimiser update for batches shaped like `batch` into one
+        CUDA graph; `train_step` replays it from then on.  Eagerly the step is ~1100 launches at ~27 us of Python / ctypes
+        each -- host-bound at 29 ms where the device needs less; a replay costs one launch.  The schedule and the step
+        counter are device-resident, so the graph holds no per-step constant.  One un-timed forward + backward runs first
+        (without an update: parameters and optimiser state are untouched) to build the lazily created constants."""
+        dev = self.device
+        self._static = {k: batch[k].to(dev).clone().contiguous() for k in self._KEYS}
+        st = self._static
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.forward_backward(st["audio_embedding"], st["image_latents"], st["text_embedding"], st["noise"], st["timesteps"])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.procs.values():          # the casts of the TRAINABLE parameters must be part of the graph, not cache hits
+            p._cache._c.clear()
+            p._kv_cache.clear()
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops._lib.launch_count()
+        with torch.cuda.graph(graph):
+            loss = self.forward_backward(st["audio_embedding"], st["image_latents"], st["text_embedding"], st["noise"],
+                                         st["timesteps"])
+            self.optimizer_step()
+            self._graph_out = {"diffusion": loss.clone(), "grad_norm": self._scalars[1:2].clone()}
+        # the capture pass launched nothing: undo its host-side bookkeeping
+        self.step_count -= 1
+        self._graph = graph
+        self.graph_launches = int(ops._lib.launch_count() - n0)      # libc2d kernels one replay launches
+
+    def _replay(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        for k in self._KEYS:
+            src, dst = batch[k], self._static[k]
+            if src.data_ptr() != dst.data_ptr():
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError(f"train_step: the captured graph expects {k} of shape {tuple(dst.shape)}, got {tuple(src.shape)}")
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        return {k: v.clone() for k, v in self._graph_out.items()}
 
     def named_grads(self) -> Dict[str, Dict[str, torch.Tensor]]:
         return {lvl: {k: self.grad[sl].view(dict(self.procs[lvl].named_parameters())[k].shape) for k, sl in self.slots[lvl].items()}

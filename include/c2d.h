@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 6   /* 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
+#define C2D_ABI_VERSION 7   /* 7: c2d_adamw_step_sched; 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
                              * 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
                              *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
@@ -291,6 +291,12 @@ int c2d_sumsq(const float* x, long long n, double* out, void* stream);
 int c2d_clip_scale(const double* sumsq, float max_norm, float* scale, float* norm_out, void* stream);
 int c2d_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+/* The same update with the schedule in device memory -- sched [sched_len][3] = (learning rate, 1 - beta1^(t+1), 1 - beta2^(t+1))
+ * of optimiser step t, *step_dev = steps taken so far (the caller increments it) -- so that the launch can live in a CUDA graph
+ * replayed once per training step. */
+int c2d_adamw_step_sched(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* sched,
+                         int sched_len, const int* step_dev, float beta1, float beta2, float eps, float weight_decay,
+                         const float* grad_scale, void* stream);
 
 /* ---- weight packing helpers (run once at load time) ------------------------------------------ */
 /* [Cout][Cin][3][3] fp32 (PyTorch/diffusers layout) -> [Cout][3][3][Cin] dtype */

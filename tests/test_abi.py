@@ -27,7 +27,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_abi_version_and_error_string():
     from clap2diffusion_b200 import _lib
-    assert _lib.lib.c2d_abi_version() == 6
+    assert _lib.lib.c2d_abi_version() == 7
     assert isinstance(_lib.last_error(), str)
 
 

@@ -532,6 +532,17 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
     return param
 
 
+def adamw_step_sched(param, grad, exp_avg, exp_avg_sq, sched, step_dev, beta1, beta2, eps, weight_decay, grad_scale=None):
+    t = min(max(int(step_dev.reshape(-1)[0]), 0), sched.shape[0] - 1)
+    lr, bc1, bc2 = (float(v) for v in sched[t])
+    g = grad * (1.0 if grad_scale is None else float(grad_scale.reshape(-1)[0]))
+    param.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(beta1).add_(g, alpha=1 - beta1)
+    exp_avg_sq.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    param.addcdiv_(exp_avg / bc1, (exp_avg_sq / bc2).sqrt() + eps, value=-lr)
+    return param
+
+
 def require_cuda(x, who):
     """The CPU host-logic tests run the product's launch sequences on torch doubles: no device requirement."""
     return None

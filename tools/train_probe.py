@@ -49,3 +49,14 @@ tot = sum(a[0] for a in agg.values())
 print(f"timed ops total {tot:.2f} ms")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
     print(f"  {k:20s} {a[0]:8.3f} ms x{a[1]}")
+
+# host-side enqueue time vs device time of N steps (is the step launch-bound?)
+torch.cuda.synchronize()
+N = 5
+t0 = time.time()
+for _ in range(N):
+    tr.train_step(batch)
+t1 = time.time()
+torch.cuda.synchronize()
+t2 = time.time()
+print(f"{N} steps: host enqueue {1e3 * (t1 - t0) / N:.1f} ms/step, until the device is idle {1e3 * (t2 - t0) / N:.1f} ms/step")
