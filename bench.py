@@ -369,8 +369,17 @@ def run_train(args):
                           "gpu_launches": int(_lib.launch_count() - l0) if args.no_train_graph else tr.graph_launches * args.steps,
                           "cuda_graph": not args.no_train_graph, "replicas_identical": same,
                           "loss": float(out["diffusion"]) * world, "grad_norm": float(out["grad_norm"])}))
+        sys.stdout.flush()
     if world > 1:
+        # the graph holds NCCL kernels: release it before the communicator goes; a watchdog turns a stuck teardown (seen
+        # once with a live graph: the line above was printed, the process never left) into a clean exit
+        import threading
+        tr.release_graph()
+        del tr
+        dist.barrier()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def _xattn_evidence(agg):

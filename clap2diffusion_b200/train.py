@@ -508,6 +508,15 @@ class Stage3Trainer:
         self._graph = graph
         self.graph_launches = int(ops._lib.launch_count() - n0)      # libc2d kernels one replay launches
 
+    def release_graph(self) -> None:
+        """Drop the captured graph (back to eager steps).  Do this before `torch.distributed.destroy_process_group()`: a live
+        graph that holds NCCL kernels keeps the communicator's teardown waiting."""
+        self._graph = None
+        self._graph_out = None
+        self._static = {}
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
     def _replay(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         for k in self._KEYS:
             src, dst = batch[k], self._static[k]
