@@ -56,6 +56,7 @@ SIGNATURES = {
     "c2d_group_norm_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _p],
     "c2d_layer_norm": [_p, _p, _p, _p, _i, _i, _f, _i, _p],
     "c2d_attention": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _f, _p, _i, _i, _p],
+    "c2d_attention_lse": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _ll, _f, _p, _p, _p, _i, _i, _p],
     "c2d_xattn_supported": [_i, _i, _i, _i, _i, _i],
     "c2d_xattn_packed_bytes": [_i, _i, _i, _i],
     "c2d_xattn_pack_kv": [_p, _p, _ll, _ll, _i, _p, _p, _ll, _ll, _i, _p, _i, _i, _i, _i, _p],
@@ -89,7 +90,7 @@ SIGNATURES = {
     "c2d_group_norm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _p],
     "c2d_layer_norm_bwd": [_p, _p, _p, _p, _p, _i, _i, _f, _i, _p],
     "c2d_geglu_bwd": [_p, _p, _p, _i, _i, _i, _p],
-    "c2d_attention_bwd": [_p] * 10 + [_i] * 5 + [_ll] * 16 + [_f, _i, _p],
+    "c2d_attention_bwd": [_p] * 10 + [_i] * 5 + [_ll] * 16 + [_f, _i, _i, _p],
     "c2d_zero_insert2x": [_p, _p, _i, _i, _i, _i, _i, _p],
     "c2d_sumpool2x2": [_p, _p, _i, _i, _i, _i, _i, _p],
     "c2d_slice_channels": [_p, _p, _p, _ll, _i, _i, _i, _i, _p],

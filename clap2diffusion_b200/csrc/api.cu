@@ -157,10 +157,20 @@ int c2d_conv3x3_down(const void* x, const void* w, const float* bias, void* y, i
 int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
                   long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
                   long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl, void* stream) {
+  return c2d_attention_lse(q, k, v, o, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, mask, nullptr, nullptr,
+                           dtype, impl, stream);
+}
+
+int c2d_attention_lse(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
+                      long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
+                      long long bsv, long long bso, float scale, const uint8_t* mask, float* lse, int* lse_written, int dtype,
+                      int impl, void* stream) {
   C2D_REQUIRE(q && k && v && o, "attention: null pointer");
+  C2D_REQUIRE((lse == nullptr) == (lse_written == nullptr), "attention: lse and lse_written go together");
+  if (lse_written) *lse_written = 0;
   C2D_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nkv > 0 && d > 0, "attention: bad dims");
   C2D_REQUIRE(dtype == C2D_F32 || dtype == C2D_BF16, "attention: bad dtype %d", dtype);
-  AttnParams p = {q, k, v, o, Nq, Nkv, d, heads, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, mask};
+  AttnParams p = {q, k, v, o, Nq, Nkv, d, heads, ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso, scale, mask, lse, lse_written};
   cudaStream_t s = (cudaStream_t)stream;
   // tiny problems / head dims beyond the flash kernels (AudioTokenGenerator single head d=768): warp-per-query kernel
   const bool vec_ok = d % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && bsq % 8 == 0 && bsk % 8 == 0 &&

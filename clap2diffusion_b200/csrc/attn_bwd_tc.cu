@@ -7,7 +7,8 @@
 //
 // Two kernels per call, both 128 x 128 score tiles, one CTA per (tile, head, batch), warp 0 = TMA producer (4-D head-view
 // tensor maps as in attn_tc.cu: head dims 40 / 80 land zero-padded in canonical 128-byte-swizzled 64-column blocks),
-// warp 1 = MMA issuer, warps 2..5 = one thread per score-tile row:
+// warp 1 = MMA issuer, warps 2..9 = two threads per score-tile row (64 of the 128 columns each: the row phase is as long
+// as the MMA phase and nothing overlaps them, S / dP being single-buffered):
 //   attn_bwd_dq_tc_kernel   CTA = 128 queries, two sweeps over the keys.  Sweep 1: S only -> online (max, sum) ->
 //       log-sum-exp per row (kept for the second kernel) and D = <dO, O>.  Sweep 2: S and dP into TMEM ->
 //       dS (bf16) written IN PLACE over S and fed to dQ += dS K as the TMEM A operand (TS form; K tile MN-major from
@@ -35,7 +36,9 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 
 constexpr int BW_T = 128;                 // tile rows (queries or keys)
 constexpr int BW_BLK = 128 * 128;         // bytes of one 128-row x 64-column bf16 block
-constexpr int BW_THREADS = 192;
+constexpr int BW_ROW_WARPS = 8;          // two warps per TMEM lane quadrant: each takes 64 of the 128 score columns of its rows
+constexpr int BW_ROW_THREADS = 32 * BW_ROW_WARPS;
+constexpr int BW_THREADS = 64 + BW_ROW_THREADS;
 
 struct BwParams {
   bf16 *dq, *dk, *dv;
@@ -44,6 +47,7 @@ struct BwParams {
   int Nq, Nkv, d, npv, heads;
   long long lddq, bsdq, lddk, bsdk, lddv, bsdv, ldo, bso, lddo, bsdo;
   float scale, scale_log2;
+  int have_lse;                           // lse[] comes from the forward pass: the dQ kernel skips its first sweep
 };
 
 __device__ __forceinline__ float bw_ex2(float x) {
@@ -60,8 +64,9 @@ __device__ __forceinline__ void bw_sts128(uint32_t addr, uint32_t a, uint32_t b,
 }
 
 // TMEM accumulator [128 lanes][npv fp32 columns] -> bf16 rows in global memory (row = lane; d % 8 == 0)
-__device__ __forceinline__ void bw_store_acc(uint32_t taddr, bf16* row_ptr, bool row_ok, int d, int npv) {
-  for (int c = 0; c < npv; c += 16) {
+// (`half`: the two warps of a lane quadrant take alternate 16-column chunks)
+__device__ __forceinline__ void bw_store_acc(uint32_t taddr, bf16* row_ptr, bool row_ok, int d, int npv, int half) {
+  for (int c = 16 * half; c < npv; c += 32) {
     uint32_t r[16];
     tmem_ld_32x16(taddr + (uint32_t)c, r);
     tmem_ld_wait();
@@ -88,7 +93,8 @@ struct BwQCfg {
   static constexpr int TILE = NBLK * BW_BLK;
   static constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_K = 2 * TILE, OFF_V = OFF_K + KS * TILE;
   static constexpr int OFF_BAR = OFF_V + KS * TILE;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_XCH = OFF_BAR + 256;                 // float2[2][128]: the two column halves' (max, sum) of sweep 1
+  static constexpr int SMEM_BYTES = OFF_XCH + 2 * 128 * 8 + 1024;
 };
 
 template <int NBLK>
@@ -111,13 +117,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BW_T, h = blockIdx.y, b = blockIdx.z;
   const int T = (p.Nkv + BW_T - 1) / BW_T;
+  const int c0 = p.have_lse ? T : 0;       // first step of the (sweep 1 | sweep 2) sequence; ring / phase counters run on c - c0
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO);
     mbar_init(qo_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(sd_full, 1);
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, BW_ROW_THREADS);
     mbar_init(dq_done, 1);
     fence_barrier_init();
   }
@@ -139,10 +146,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
     __syncwarp();
-    for (int c = 0; c < 2 * T; ++c) {
-      const int s = c % KS, t = c < T ? c : c - T;
+    for (int c = c0; c < 2 * T; ++c) {
+      const int ci = c - c0;
+      const int s = ci % KS, t = c < T ? c : c - T;
       const bool sweep2 = c >= T;
-      mbar_wait_backoff(&kv_empty[s], ((uint32_t)(c / KS) & 1u) ^ 1u);
+      mbar_wait_backoff(&kv_empty[s], ((uint32_t)(ci / KS) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[s], sweep2 ? 2 * Cfg::TILE : Cfg::TILE);
 #pragma unroll
@@ -161,17 +169,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint64_t do_desc = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_DO));
     const int ksteps = (p.d + 15) >> 4;
     mbar_wait(qo_full, 0);
-    for (int c = 0; c < 2 * T; ++c) {
-      const int s = c % KS;
+    for (int c = c0; c < 2 * T; ++c) {
+      const int ci = c - c0;
+      const int s = ci % KS;
       const bool sweep2 = c >= T;
-      if (c > 0) {
-        mbar_wait(ds_full, (uint32_t)(c - 1) & 1u);       // the row warps are done with S / dP of tile c-1 (sweep 2: dS written)
+      if (c > c0) {
+        mbar_wait(ds_full, (uint32_t)(ci - 1) & 1u);      // the row warps are done with S / dP of tile c-1 (sweep 2: dS written)
         tc_fence_after();
         if (c > T) {
           // dQ += dS(c-1) K(c-1): dS is bf16 in place over S (TS form), K tile MN-major from the stage of c-1.  Issued (and
           // its stage released) BEFORE waiting for this tile's operands: with a single stage the producer needs it.
           if (elect_one()) {
-            const int sp = (c - 1) % KS;
+            const int sp = (ci - 1) % KS;
             const uint64_t kmn = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_K + sp * Cfg::TILE), BW_BLK, 1024);
 #pragma unroll
             for (int kk = 0; kk < BW_T / 16; ++kk)
@@ -181,7 +190,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           __syncwarp();
         }
       }
-      mbar_wait(&kv_full[s], (uint32_t)(c / KS) & 1u);
+      mbar_wait(&kv_full[s], (uint32_t)(ci / KS) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t kd = make_desc_k_sw128(smem_u32(smem + Cfg::OFF_K + s * Cfg::TILE));
@@ -201,10 +210,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
     }
     // last tile's dQ contribution
-    mbar_wait(ds_full, (uint32_t)(2 * T - 1) & 1u);
+    mbar_wait(ds_full, (uint32_t)(2 * T - 1 - c0) & 1u);
     tc_fence_after();
     if (elect_one()) {
-      const int sp = (2 * T - 1) % KS;
+      const int sp = (2 * T - 1 - c0) % KS;
       const uint64_t kmn = make_desc_mn_sw128(smem_u32(smem + Cfg::OFF_K + sp * Cfg::TILE), BW_BLK, 1024);
 #pragma unroll
       for (int kk = 0; kk < BW_T / 16; ++kk)
@@ -213,13 +222,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     __syncwarp();
   } else {
-    // ===================== row warps (thread = query row) =====================
-    const int quad = warp & 3;
+    // ===================== row warps (two threads per query row: score columns [64 half, 64 half + 64)) =====================
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int qrow = q0 + row;
     const bool row_ok = qrow < p.Nq;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const long long sidx = ((long long)b * p.heads + h) * p.Nq + qrow;
+    float2* xch = reinterpret_cast<float2*>(smem + Cfg::OFF_XCH);
+    const int col0 = half * 64;
     // D = <dO, O> from global memory while the first tiles are in flight
     float dl = 0.f;
     if (row_ok) {
@@ -236,18 +247,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           dl = fmaf(fa.x, fg.x, fmaf(fa.y, fg.y, dl));
         }
       }
-      p.delta[sidx] = dl;
+      if (half == 0) p.delta[sidx] = dl;
     }
     float m = -FLT_MAX, l = 0.f, lse = 0.f;
-    for (int c = 0; c < 2 * T; ++c) {
+    if (p.have_lse && row_ok) lse = p.lse[sidx];
+    for (int c = c0; c < 2 * T; ++c) {
       const bool sweep2 = c >= T;
       const int t = sweep2 ? c - T : c;
       const int kvalid = min(BW_T, p.Nkv - t * BW_T);
-      mbar_wait(sd_full, (uint32_t)c & 1u);
+      mbar_wait(sd_full, (uint32_t)(c - c0) & 1u);
       tc_fence_after();
       if (!sweep2) {
 #pragma unroll 1
-        for (int cc = 0; cc < BW_T; cc += 32) {
+        for (int cc = col0; cc < col0 + 64; cc += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_s + lane_off + (uint32_t)cc, r);
           tmem_ld_wait();
@@ -262,20 +274,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           l = l * bw_ex2(m - mx) + acc;
           m = mx;
         }
-        if (c == T - 1) {
-          lse = m + __log2f(l);
-          if (row_ok) p.lse[sidx] = lse;
-        }
         tc_fence_before();
         mbar_arrive(ds_full);
+        if (c == T - 1) {
+          // fold the two column halves' (max, sum): log-sum-exp of the whole row
+          xch[half * 128 + row] = make_float2(m, l);
+          asm volatile("bar.sync 1, %0;" ::"n"(BW_ROW_THREADS) : "memory");
+          const float2 o = xch[(half ^ 1) * 128 + row];
+          const float mm = fmaxf(m, o.x);
+          const float ll = (l > 0.f ? l * bw_ex2(m - mm) : 0.f) + (o.y > 0.f ? o.y * bw_ex2(o.x - mm) : 0.f);
+          lse = mm + __log2f(ll);
+          if (row_ok && half == 0) p.lse[sidx] = lse;
+        }
       } else {
-#pragma unroll 1
-        for (int cc = 0; cc < BW_T; cc += 32) {
+        // dS goes IN PLACE over S (packed: 32 keys -> 16 columns at cc / 2): the upper half's packed columns 32..63 lie over
+        // S columns the lower-half warp of the same rows still has to read, so both warps load their whole halves first
+        uint32_t pk[2][16];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int cc = col0 + u * 32;
           uint32_t rs[32], rd[32];
           tmem_ld_32x32(tmem_s + lane_off + (uint32_t)cc, rs);
           tmem_ld_32x32(tmem_dp + lane_off + (uint32_t)cc, rd);
           tmem_ld_wait();
-          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float d0 = 0.f, d1 = 0.f;
@@ -283,12 +304,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               d0 = bw_ex2(fmaf(__uint_as_float(rs[i]), p.scale_log2, -lse)) * (__uint_as_float(rd[i]) - dl) * p.scale;
             if (row_ok && cc + i + 1 < kvalid)
               d1 = bw_ex2(fmaf(__uint_as_float(rs[i + 1]), p.scale_log2, -lse)) * (__uint_as_float(rd[i + 1]) - dl) * p.scale;
-            pk[i >> 1] = bw_pack(d0, d1);
+            pk[u][i >> 1] = bw_pack(d0, d1);
           }
-          // 32 keys -> 16 packed columns at [cc / 2, cc / 2 + 16) of the S region: ascending cc never overtakes the reads
+        }
+        tc_fence_before();
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");       // the two warps of this lane quadrant
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int cc = col0 + u * 32;
           uint32_t lo[8], hi[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { lo[i] = pk[i]; hi[i] = pk[8 + i]; }
+          for (int i = 0; i < 8; ++i) { lo[i] = pk[u][i]; hi[i] = pk[u][8 + i]; }
           tmem_st_32x8(tmem_s + lane_off + (uint32_t)(cc >> 1), lo);
           tmem_st_32x8(tmem_s + lane_off + (uint32_t)(cc >> 1) + 8, hi);
         }
@@ -299,7 +326,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     mbar_wait(dq_done, 0);
     tc_fence_after();
-    bw_store_acc(tmem_acc + lane_off, p.dq + (long long)b * p.bsdq + (long long)qrow * p.lddq + (long long)h * p.d, row_ok, p.d, p.npv);
+    bw_store_acc(tmem_acc + lane_off, p.dq + (long long)b * p.bsdq + (long long)qrow * p.lddq + (long long)h * p.d, row_ok, p.d, p.npv, half);
   }
   tc_fence_before();
   __syncthreads();
@@ -351,7 +378,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qo_full[i], 1); mbar_init(&qo_empty[i], 1); }
     mbar_init(sd_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, BW_ROW_THREADS);
     mbar_init(pds_free, 1);
     mbar_init(acc_done, 1);
     fence_barrier_init();
@@ -453,8 +480,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     __syncwarp();
   } else {
-    // ===================== row warps (thread = query row of the current tile; key row in the epilogue) =====================
-    const int quad = warp & 3;
+    // ===================== row warps (two threads per query row of the current tile, 64 keys each; key row in the epilogue) =====
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int kvalid = min(BW_T, p.Nkv - k0);
@@ -474,7 +501,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (i > 0) mbar_wait(pds_free, (uint32_t)(i - 1) & 1u);      // the accumulation MMAs of tile i-1 have read P / dS
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < BW_T; cc += 32) {
+      for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
         uint32_t rs[32], rd[32];
         tmem_ld_32x32(tmem_s + lane_off + (uint32_t)cc, rs);
         if (HAS_DS) tmem_ld_32x32(tmem_dp + lane_off + (uint32_t)cc, rd);
@@ -507,9 +534,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int krow = k0 + row;
     const bool ok = krow < p.Nkv;
     if (HAS_P)
-      bw_store_acc(tmem_dv + lane_off, p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + (long long)h * p.d, ok, p.d, p.npv);
+      bw_store_acc(tmem_dv + lane_off, p.dv + (long long)b * p.bsdv + (long long)krow * p.lddv + (long long)h * p.d, ok, p.d, p.npv, half);
     if (HAS_DS)
-      bw_store_acc(tmem_dk + lane_off, p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + (long long)h * p.d, ok, p.d, p.npv);
+      bw_store_acc(tmem_dk + lane_off, p.dk + (long long)b * p.bsdk + (long long)krow * p.lddk + (long long)h * p.d, ok, p.d, p.npv, half);
   }
   tc_fence_before();
   __syncthreads();
@@ -536,6 +563,7 @@ struct AttnBwdArgs {      // mirrors c2d_attention_bwd
   int B, heads, Nq, Nkv, d;
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv;
   float scale;
+  int have_lse;
 };
 
 bool attention_bwd_tc_supported(const AttnBwdArgs& a) {
@@ -586,6 +614,7 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t s) {
   p.lddq = a.lddq; p.bsdq = a.bsdq; p.lddk = a.lddk; p.bsdk = a.bsdk; p.lddv = a.lddv; p.bsdv = a.bsdv;
   p.ldo = a.ldo; p.bso = a.bso; p.lddo = a.lddo; p.bsdo = a.bsdo;
   p.scale = a.scale; p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.have_lse = a.have_lse;
   if (a.d <= 64) return attention_bwd_tc_n<1>(a, p, s);
   return a.d <= 128 ? attention_bwd_tc_n<2>(a, p, s) : attention_bwd_tc_n<3>(a, p, s);
 }

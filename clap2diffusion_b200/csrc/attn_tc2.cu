@@ -38,6 +38,7 @@ constexpr float A2_RESCALE_LOG2 = 8.f;                  // rescale O only when t
 
 struct Attn2Params {
   bf16* o;
+  float* lse;                   // optional [B][heads][Nq]: m + log2(sum) of the scaled scores (training forward)
   int Nq, Nkv, d, npv;
   long long ldo, bso;
   float scale_log2;
@@ -394,7 +395,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&o_done[qt], (uint32_t)(ntiles - 1) & 1u);
     tc_fence_after();
     const int qrow = q0 + qt * A2_BQ + row;
-    const float inv = 1.f / ((l0 + l1) + (l2 + l3));
+    const float lsum = (l0 + l1) + (l2 + l3);
+    const float inv = 1.f / lsum;
+    if (p.lse && qrow < p.Nq) p.lse[((long long)b * gridDim.y + h) * p.Nq + qrow] = m_ref + __log2f(lsum);
     bf16* orow = p.o + (long long)b * p.bso + (long long)qrow * p.ldo + (long long)h * p.d;
     for (int c = 0; c < p.npv; c += 16) {
       uint32_t r[16];
@@ -446,6 +449,8 @@ int attention_tc2(const AttnParams& p, int B, cudaStream_t s) {
   if (rc) return rc;
   Attn2Params ap;
   ap.o = reinterpret_cast<bf16*>(p.o);
+  ap.lse = p.lse;
+  if (p.lse && p.lse_written) *p.lse_written = 1;
   ap.Nq = p.Nq; ap.Nkv = p.Nkv; ap.d = p.d; ap.npv = (p.d + 15) & ~15;
   ap.ldo = p.ldo; ap.bso = p.bso;
   ap.scale_log2 = p.scale * 1.4426950408889634f;

@@ -207,6 +207,10 @@ struct AttnParams {
   long long ldq, ldk, ldv, ldo, bsq, bsk, bsv, bso;   // row / batch strides in elements
   float scale;
   const uint8_t* mask;   // [B][Nkv] (1 = keep) or null
+  // optional (training forward): per-row log2-domain log-sum-exp of the scaled scores, [B][heads][Nq]; the kernel that
+  // produces it sets *lse_written (host) -- kernels without the output leave both untouched
+  float* lse;
+  int* lse_written;
 };
 
 // optional inputs / outputs of the tcgen05 GEMM (see c2d_linear_ex)

@@ -613,6 +613,7 @@ struct AttnBwdArgs {
   int B, heads, Nq, Nkv, d;
   long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv;
   float scale;
+  int have_lse;
 };
 bool attention_bwd_tc_supported(const AttnBwdArgs& a);
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t s);
@@ -670,7 +671,7 @@ int c2d_attention_bwd(const void* q, const void* k, const void* v, const void* o
                       float* lse_ws, float* delta_ws, int B, int heads, int Nq, int Nkv, int d, long long ldq, long long ldk,
                       long long ldv, long long ldo, long long lddo, long long lddq, long long lddk, long long lddv,
                       long long bsq, long long bsk, long long bsv, long long bso, long long bsdo, long long bsdq,
-                      long long bsdk, long long bsdv, float scale, int dtype, void* stream) {
+                      long long bsdk, long long bsdv, float scale, int have_lse, int dtype, void* stream) {
   C2D_REQUIRE(q && k && v && o && dout && dq && dk && dv && lse_ws && delta_ws, "attention_bwd: null pointer");
   C2D_REQUIRE(B > 0 && heads > 0 && Nq > 0 && Nkv > 0 && d > 0 && d <= AB_MAXD, "attention_bwd: bad dims (head dim <= %d)", AB_MAXD);
   AttnBwdParams p = {q, k, v, o, dout, dq, dk, dv, lse_ws, delta_ws, Nq, Nkv, d, heads,
@@ -678,7 +679,7 @@ int c2d_attention_bwd(const void* q, const void* k, const void* v, const void* o
   if (dtype == C2D_F32) return attention_bwd_t<float>(p, B, (cudaStream_t)stream);
   if (dtype == C2D_BF16) {
     const AttnBwdArgs a = {q, k, v, o, dout, dq, dk, dv, lse_ws, delta_ws, B, heads, Nq, Nkv, d, ldq, ldk, ldv, ldo, lddo, lddq, lddk,
-                           lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv, scale};
+                           lddv, bsq, bsk, bsv, bso, bsdo, bsdq, bsdk, bsdv, scale, have_lse};
     if (attention_bwd_tc_supported(a)) return attention_bwd_tc(a, (cudaStream_t)stream);      // tensor cores
     return attention_bwd_t<bf16>(p, B, (cudaStream_t)stream);                                 // head dims > 128: FFMA kernels
   }

@@ -5,6 +5,7 @@ Layout: activations are channels-last token tensors [B, N, C] (N = H*W); see c2d
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
@@ -305,9 +306,11 @@ def layer_norm(x, gamma, beta, eps=1e-5, *, out=None):
     return out
 
 
-def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, out=None, impl=IMPL_AUTO):
+def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, out=None, impl=IMPL_AUTO, lse=None):
     """softmax(q k^T * scale) v per head.  q [B,Nq,heads*d], k/v [B,Nkv,heads*d]; strided views (e.g. slices
-    of a packed QKV buffer) are accepted as long as the inner dim is contiguous."""
+    of a packed QKV buffer) are accepted as long as the inner dim is contiguous.
+    lse (training forward): fp32 [B,heads,Nq] buffer for the rows' log-sum-exp; the call then returns (out, written) where
+    `written` tells whether the kernel that ran produces it (attention_bwd(..., lse=...) skips a sweep when it did)."""
     _dev(q)
     B, Nq, C = q.shape
     Nkv = k.shape[1]
@@ -321,6 +324,15 @@ def attention(q, k, v, heads: int, *, scale: Optional[float] = None, mask=None, 
         scale = d ** -0.5
     if mask is not None:
         assert mask.dtype in (torch.bool, torch.uint8) and mask.is_contiguous() and tuple(mask.shape) == (B, Nkv)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and tuple(lse.shape) == (B, heads, Nq)
+        written = ctypes.c_int(0)
+        with _Timed(4.0 * B * heads * Nq * Nkv * d, (2 * B * Nq * C + 2 * B * Nkv * C) * q.element_size()):
+            check(lib.c2d_attention_lse(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nkv, d,
+                                        q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0),
+                                        v.stride(0), out.stride(0), float(scale), _ptr(mask), lse.data_ptr(), ctypes.byref(written),
+                                        _dt(q), impl, _stream()), "attention")
+        return out, bool(written.value)
     with _Timed(4.0 * B * heads * Nq * Nkv * d, (2 * B * Nq * C + 2 * B * Nkv * C) * q.element_size()):
         check(lib.c2d_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nkv, d,
                                 q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0),
@@ -836,9 +848,10 @@ def geglu_bwd(ag, dy, *, out=None):
     return out
 
 
-def attention_bwd(q, k, v, o, dout, heads: int, dq, dk, dv, *, scale: Optional[float] = None):
+def attention_bwd(q, k, v, o, dout, heads: int, dq, dk, dv, *, scale: Optional[float] = None, lse=None):
     """Adjoint of ops.attention.  q [B,Nq,h*d], k / v [B,Nkv,h*d], o / dout [B,Nq,h*d]; dq / dk / dv are caller-provided
-    (possibly strided) views with the same logical shapes as q / k / v."""
+    (possibly strided) views with the same logical shapes as q / k / v.  lse: the forward pass's log-sum-exp
+    (ops.attention(..., lse=buf) that reported `written`): the tensor-core kernels skip their first sweep over the keys."""
     _dev(q)
     B, Nq, C = q.shape
     Nkv = k.shape[1]
@@ -848,12 +861,16 @@ def attention_bwd(q, k, v, o, dout, heads: int, dq, dk, dv, *, scale: Optional[f
     if scale is None:
         scale = d ** -0.5
     ws = torch.empty(2, B, heads, Nq, device=q.device, dtype=torch.float32)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and tuple(lse.shape) == (B, heads, Nq)
+    lse_ptr = ws[0].data_ptr() if lse is None else lse.data_ptr()
     with _Timed(10.0 * B * heads * Nq * Nkv * d, _nb(q, k, v, o, dout, dq, dk, dv)):
         check(lib.c2d_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), dq.data_ptr(),
-                                    dk.data_ptr(), dv.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), B, heads, Nq, Nkv, d,
+                                    dk.data_ptr(), dv.data_ptr(), lse_ptr, ws[1].data_ptr(), B, heads, Nq, Nkv, d,
                                     q.stride(1), k.stride(1), v.stride(1), o.stride(1), dout.stride(1), dq.stride(1), dk.stride(1),
                                     dv.stride(1), q.stride(0), k.stride(0), v.stride(0), o.stride(0), dout.stride(0), dq.stride(0),
-                                    dk.stride(0), dv.stride(0), float(scale), _dt(q), _stream()), "attention_bwd")
+                                    dk.stride(0), dv.stride(0), float(scale), int(lse is not None), _dt(q), _stream()),
+              "attention_bwd")
     return dq, dk, dv
 
 

@@ -181,7 +181,9 @@ class FrozenUNetGrad:
     def _self_attention(self, tp: _Tape, site, x):
         C, heads = x.shape[-1], site.heads
         qkv = self._lin(tp, x, f"{site.name}.wqkv", w=site.wqkv)
-        o = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale=site.scale)
+        # the long-sequence forward kernel also leaves the rows' log-sum-exp for the adjoint (one sweep over the keys less)
+        lse = torch.empty(x.shape[0], heads, x.shape[1], device=x.device, dtype=torch.float32)
+        o, have_lse = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale=site.scale, lse=lse)
 
         def bwd():
             go = tp.pop(o)
@@ -189,7 +191,8 @@ class FrozenUNetGrad:
                 return
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, go, heads,
-                              dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:], scale=site.scale)
+                              dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:], scale=site.scale,
+                              lse=lse if have_lse else None)
             tp.add_grad(qkv, dqkv)
         tp.ops.append(bwd)
         return o

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 7   /* 7: c2d_adamw_step_sched; 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
+#define C2D_ABI_VERSION 7   /* 7: c2d_adamw_step_sched, c2d_attention_lse, have_lse argument of c2d_attention_bwd; 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
                              * 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
                              *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
@@ -151,6 +151,13 @@ int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, i
                   long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
                   long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl,
                   void* stream);
+/* Training forward: the same call with an optional by-product for c2d_attention_bwd -- lse [B][heads][Nq] fp32, the per-row
+ * log-sum-exp of the scaled scores in the log2 domain (max + log2(sum 2^(s - max)), s = scale * log2(e) * q.k).  Only the
+ * long-sequence tcgen05 kernel (head_dim <= 64, Nkv > 128) produces it; *lse_written (host) says whether this call did. */
+int c2d_attention_lse(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
+                      long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
+                      long long bsv, long long bso, float scale, const uint8_t* mask, float* lse, int* lse_written, int dtype,
+                      int impl, void* stream);
 
 /* ---- fused cross-attention site (bf16 / tcgen05 only).  Replaces, in ONE kernel per denoising step, the reference's
  *  attn.to_q + head_to_batch_dim + get_attention_scores + bmm + batch_to_head_dim
@@ -261,12 +268,14 @@ int c2d_layer_norm_bwd(const void* x, const void* dy, const float* gamma, const 
 /* adjoint of c2d_geglu: ag [M][2F] = [a | g], dy [M][F] -> dag [M][2F] */
 int c2d_geglu_bwd(const void* ag, const void* dy, void* dag, int M, int F, int dtype, void* stream);
 /* flash-attention adjoint (recompute form) of c2d_attention: dq, dk, dv from q, k, v, o, dout.  Row strides ld*, batch
- * strides bs* in elements (packed QKV views welcome); lse_ws / delta_ws: fp32 [B][heads][Nq] scratch each; d <= 160. */
+ * strides bs* in elements (packed QKV views welcome); lse_ws / delta_ws: fp32 [B][heads][Nq] scratch each; d <= 160.
+ * have_lse != 0: lse_ws already holds the forward pass's log-sum-exp (c2d_attention_lse reported *lse_written): the bf16
+ * tensor-core kernels then skip their first sweep over the keys. */
 int c2d_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, void* dq, void* dk, void* dv,
                       float* lse_ws, float* delta_ws, int B, int heads, int Nq, int Nkv, int d, long long ldq, long long ldk,
                       long long ldv, long long ldo, long long lddo, long long lddq, long long lddk, long long lddv,
                       long long bsq, long long bsk, long long bsv, long long bso, long long bsdo, long long bsdq,
-                      long long bsdk, long long bsdv, float scale, int dtype, void* stream);
+                      long long bsdk, long long bsdv, float scale, int have_lse, int dtype, void* stream);
 /* z[B][2H][2W][C]: x at the even positions, zeros elsewhere (adjoint of the stride-2 gather);
  * y[B][H][W][C] = 2x2 block sums of x[B][2H][2W][C] (adjoint of the nearest 2x upsample);
  * y[rows][Cs] = x[rows][c0 : c0+Cs] (+ add) (adjoint of the channel concat) */

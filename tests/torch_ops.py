@@ -172,7 +172,9 @@ def layer_norm(x, gamma, beta, eps=1e-5, *, out=None):
     return F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(x.dtype)
 
 
-def attention(q, k, v, heads, *, scale=None, mask=None, out=None, impl=0):
+def attention(q, k, v, heads, *, scale=None, mask=None, out=None, impl=0, lse=None):
+    if lse is not None:          # the double never produces the by-product: the adjoint recomputes it
+        return attention(q, k, v, heads, scale=scale, mask=mask, out=out, impl=impl), False
     B, Nq, C = q.shape
     d = C // heads
     scale = d ** -0.5 if scale is None else scale
@@ -444,7 +446,7 @@ def geglu_bwd(ag, dy, *, out=None):
     return _vjp(lambda t: t[..., :Fh] * F.gelu(t[..., Fh:]), [ag], dy)[0].to(ag.dtype)
 
 
-def attention_bwd(q, k, v, o, dout, heads, dq, dk, dv, *, scale=None):
+def attention_bwd(q, k, v, o, dout, heads, dq, dk, dv, *, scale=None, lse=None):
     def f(qq, kk, vv):
         B, Nq, C = qq.shape
         d = C // heads
