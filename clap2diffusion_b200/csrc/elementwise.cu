@@ -253,10 +253,25 @@ __global__ void audio_context_kernel(const T* __restrict__ ehs, const T* __restr
   int b = blockIdx.x;
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const T* a = audio + (long long)b * K * Da;
+  const bool vec = (Da % 8 == 0) && (D % 8 == 0) && ((reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(audio) |
+                                                     reinterpret_cast<uintptr_t>(ehs) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   for (int o = warp; o < K * Hb; o += nwarp) {
     int k = o / Hb, j = o - k * Hb;
     float acc = 0.f;
-    for (int i = lane; i < Da; i += 32) acc += to_f<T>(w1[(long long)j * Da + i]) * to_f<T>(a[(long long)k * Da + i]);
+    if (vec) {          // 16-byte loads, all of a lane's chunks in flight (the scalar loop was one load latency per element)
+      const T* wr = w1 + (long long)j * Da;
+      const T* ar = a + (long long)k * Da;
+#pragma unroll 4
+      for (int i = lane * 8; i < Da; i += 256) {
+        float fw[8], fa[8];
+        Vec8<T>::load(wr + i, fw);
+        Vec8<T>::load(ar + i, fa);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(fw[u], fa[u], acc);
+      }
+    } else {
+      for (int i = lane; i < Da; i += 32) acc += to_f<T>(w1[(long long)j * Da + i]) * to_f<T>(a[(long long)k * Da + i]);
+    }
     acc = warp_sum(acc);
     if (lane == 0) g[o] = gelu_erf(acc + b1[j]);
   }
@@ -283,7 +298,18 @@ __global__ void audio_context_kernel(const T* __restrict__ ehs, const T* __restr
   if (mode == C2D_AUDIO_ADD) {
     float gate = 1.f / (1.f + expf(-alpha[0]));
     T* o = out + (long long)b * Tn * D;
-    for (int i = threadIdx.x; i < Tn * D; i += blockDim.x) o[i] = from_f<T>(to_f<T>(e[i]) + gate * v[i % D]);
+    if (vec) {
+      for (int i = threadIdx.x * 8; i < Tn * D; i += blockDim.x * 8) {
+        float f[8];
+        Vec8<T>::load(e + i, f);
+        const int d0 = i % D;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = fmaf(gate, v[d0 + u], f[u]);
+        Vec8<T>::store(o + i, f);
+      }
+    } else {
+      for (int i = threadIdx.x; i < Tn * D; i += blockDim.x) o[i] = from_f<T>(to_f<T>(e[i]) + gate * v[i % D]);
+    }
   } else {
     T* o = out + (long long)b * (Tn + P) * D;
     for (int i = threadIdx.x; i < Tn * D; i += blockDim.x) o[i] = e[i];
