@@ -122,8 +122,13 @@ __device__ __forceinline__ void ln_row_coeffs(const TcParams& p, int m, float& r
 // instructions per useful one (ncu on M = 2^20, N = 288, K = 96: 445 warp instructions per chunk, 70 of them data
 // movement or arithmetic), which bounds every GEMM whose main loop is short (K <= 384: the CLAP tower, the UNet's
 // 64 x 64-level projections).  `srow0` = this lane's first staged row at its column group, `ncol_ok` = the group lies in N.
+template <bool STATS = false>
 __device__ __forceinline__ void drain32_fast(const float* srow0, int pitch, bf16* yp, long long ldy, const bf16* rp, long long ldr,
-                                             bool ncol_ok) {
+                                             bool ncol_ok, float* ssum = nullptr, float* ssq = nullptr) {
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+  }
   if (!ncol_ok) return;
   uint4 res[4];
   if (rp) {
@@ -141,6 +146,10 @@ __device__ __forceinline__ void drain32_fast(const float* srow0, int pitch, bf16
       for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
     }
     Vec8<bf16>::store(yp + (long long)u * 8 * ldy, v);
+    if (STATS) {           // per-channel (sum, sum of squares) of what was stored, for the consuming GroupNorm
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
+    }
   }
 }
 
@@ -1042,6 +1051,21 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int mrow0 = m0 + q * 32;
       const int n = nbase + c * 32 + g * 8;
       const int nvalid = ncols - n;
+      if (vec_y && (!p.residual || vec_r) && (ncols % 8 == 0) && m0 + TC_BM <= p.M) {
+        const long long row = mrow0 + rsub;
+        if (p.stats) {
+          float fs[8], fq[8];
+          drain32_fast<true>(stage + (size_t)rsub * Cfg::EPI_PITCH + g * 8, Cfg::EPI_PITCH, p.y + row * p.ldy + n, p.ldy,
+                             p.residual ? p.residual + row * p.ldr + n : nullptr, p.ldr, n < ncols, fs, fq);
+          const int bimg = mrow0 / p.stats_rows;
+          stats_commit(fs, fq, lane, p.stats + ((size_t)bimg * ncols + (size_t)(n < ncols ? n : 0)) * 2, nvalid);
+        } else {
+          drain32_fast(stage + (size_t)rsub * Cfg::EPI_PITCH + g * 8, Cfg::EPI_PITCH, p.y + row * p.ldy + n, p.ldy,
+                       p.residual ? p.residual + row * p.ldr + n : nullptr, p.ldr, n < ncols);
+        }
+        __syncwarp();
+        continue;
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int m = mrow0 + u * 8 + rsub;
