@@ -92,6 +92,27 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict
   const uint32_t row_off = (uint32_t)tid * 128u, sw = (uint32_t)(tid & 7);
   const uint32_t q_row = smem_u32(smem + WT_OFF_Q) + row_off, k_row = smem_u32(smem + WT_OFF_K) + row_off,
                  v_row = smem_u32(smem + WT_OFF_V) + row_off;
+  // Cooperative gather / scatter mapping: FOUR consecutive lanes move the (up to four) 16-byte chunks of one token's
+  // head slice, a warp instruction covers 8 tokens (8 cache lines) instead of 32 tokens at one chunk each (32 lines:
+  // the LSU wavefronts of the row-per-thread gather bounded the kernel -- ncu: mio-throttle 5.8 / issue).  Thread tid
+  // serves chunk gc of tile rows gr0 + 32 j, j = 0..3.
+  const int gc = tid & 3, gr0 = tid >> 2;
+  const bool g_act = gc < NCH;
+  long long gtok[4];
+  bool gval[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = gr0 + 32 * j, rws = r >> 6, ri = r & 63;
+    const int rgw = blockIdx.x * 2 + rws;
+    gval[j] = rgw < total_windows;
+    const int rb = gval[j] ? rgw / nwin : 0, rwin = gval[j] ? rgw % nwin : 0;
+    const int ry = ((rwin / nw) * 8 + (ri >> 3) + shift) % H, rx = ((rwin % nw) * 8 + (ri & 7) + shift) % W;
+    gtok[j] = (long long)rb * H * W + (long long)ry * W + rx;
+  }
+  const uint32_t g_off = (uint32_t)gr0 * 128u + (((uint32_t)gc ^ (uint32_t)(gr0 & 7)) << 4);    // (gr0 + 32 j) & 7 == gr0 & 7
+  // O staging over the V tile (dead once P V has retired; its padding columns only feed unused output columns)
+  const uint32_t so_w = smem_u32(smem + WT_OFF_V) + (uint32_t)tid * 64u;
+  const uint32_t so_r = smem_u32(smem + WT_OFF_V) + (uint32_t)gr0 * 64u + (uint32_t)gc * 16u;
   auto sts = [](uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
   };
@@ -126,23 +147,25 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict
   for (int hh = 0; hh < WT_HPC; ++hh) {
     const int head = h0 + hh;
     const uint32_t ph = (uint32_t)hh & 1u;
-    // ---- gather this token's q / k / v of the head into the swizzled operand tiles
-    {
-      const bf16* row = qkv + tok * 3 * C + head * D;
-      uint4 rq[NCH], rk[NCH], rv[NCH];
+    // ---- gather q / k / v of the head into the swizzled operand tiles
+    if (g_act) {
+      uint4 rq[4], rk[4], rv[4];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        rq[c] = rk[c] = rv[c] = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) {
-          rq[c] = __ldg(reinterpret_cast<const uint4*>(row) + c);
-          rk[c] = __ldg(reinterpret_cast<const uint4*>(row + C) + c);
-          rv[c] = __ldg(reinterpret_cast<const uint4*>(row + 2 * C) + c);
+      for (int j = 0; j < 4; ++j) {
+        rq[j] = rk[j] = rv[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (gval[j]) {
+          const uint4* src = reinterpret_cast<const uint4*>(qkv + gtok[j] * 3 * C + head * D) + gc;
+          rq[j] = __ldg(src);
+          rk[j] = __ldg(src + (C >> 3));
+          rv[j] = __ldg(src + (C >> 2));
         }
       }
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const uint32_t o = ((uint32_t)c ^ sw) << 4;
-        sts(q_row + o, rq[c]); sts(k_row + o, rk[c]); sts(v_row + o, rv[c]);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t o = g_off + (uint32_t)j * 4096u;                   // 32 rows further
+        sts(smem_u32(smem + WT_OFF_Q) + o, rq[j]);
+        sts(smem_u32(smem + WT_OFF_K) + o, rk[j]);
+        sts(smem_u32(smem + WT_OFF_V) + o, rv[j]);
       }
     }
     // the head's bias [64][64] -> shared memory with coalesced loads: a thread reading its own 256-byte row from global
@@ -233,20 +256,31 @@ window_attention_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict
       tmem_ld_32x32(tmem_o, r);
       tmem_ld_wait();
       const float inv = 1.f / sum;
-      if (valid) {
-        bf16* orow = out + tok * C + head * D;
+      // rows -> shared memory (over the V tile: P V has retired) -> the cooperative mapping of the gather
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < NCH; ++c) {
+        uint4 o4;
+        o4.x = wt_pack(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
+        o4.y = wt_pack(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
+        o4.z = wt_pack(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
+        o4.w = wt_pack(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
+        sts(so_w + (uint32_t)c * 16u, o4);
+      }
+    }
+    tc_fence_before();     // the next head's score MMA overwrites S / O: ordered by the barriers below
+    __syncthreads();
+    if (g_act) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (gval[j]) {
           uint4 o4;
-          o4.x = wt_pack(__uint_as_float(r[8 * c]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
-          o4.y = wt_pack(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
-          o4.z = wt_pack(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
-          o4.w = wt_pack(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 8 * c) = o4;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o4.x), "=r"(o4.y), "=r"(o4.z), "=r"(o4.w)
+                       : "r"(so_r + (uint32_t)j * 2048u));
+          *(reinterpret_cast<uint4*>(out + gtok[j] * C + head * D) + gc) = o4;
         }
       }
     }
-    tc_fence_before();     // the next head's score MMA overwrites S / O: ordered by the __syncthreads of its gather
+    __syncthreads();       // the staged rows are read: the next head's gather may overwrite the V tile
   }
   tc_fence_before();
   __syncthreads();
