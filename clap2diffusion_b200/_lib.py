@@ -87,7 +87,7 @@ SIGNATURES = {
     "c2d_patch_merge": [_p, _p, _i, _i, _i, _i, _i, _p],
     "c2d_token_mean": [_p, _p, _i, _i, _i, _i, _p],
     "c2d_l2_normalize": [_p, _p, _i, _i, _f, _p],
-    "c2d_group_norm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _p],
+    "c2d_group_norm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _i, _p],
     "c2d_layer_norm_bwd": [_p, _p, _p, _p, _p, _i, _i, _f, _i, _p],
     "c2d_geglu_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "c2d_attention_bwd": [_p] * 10 + [_i] * 5 + [_ll] * 16 + [_f, _i, _i, _p],

@@ -448,19 +448,24 @@ gn_bwd_pass_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, cons
   }
 }
 
-// ws: caller-zeroed, B * C * 2 int64 (channel statistics of x) followed by B * C * 2 doubles (adjoint sums)
+// ws: caller-zeroed, B * C * 2 int64 (channel statistics of x) followed by B * C * 2 doubles (adjoint sums); x_stats
+// (optional): the channel statistics the forward pass already produced (c2d_channel_stats / a GEMM epilogue) -- pass 1 is
+// then skipped
 int group_norm_bwd_fast(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
-                        int B, int HW, int C, int groups, float eps, int silu, cudaStream_t s) {
+                        const long long* x_stats, int B, int HW, int C, int groups, float eps, int silu, cudaStream_t s) {
   const int threads = gn2_threads(C), rif = threads / (C / 8);
   dim3 grid;
   int rpc;
   gn2_grid(B, HW, rif, &grid, &rpc);
   const size_t smem = (size_t)rif * C * 2 * sizeof(float);
   if (smem > 48 * 1024) return -1;
-  long long* st = reinterpret_cast<long long*>(ws);
-  double* gst = reinterpret_cast<double*>(st + (size_t)B * C * 2);
-  chan_stats_kernel<bf16><<<grid, threads, smem, s>>>((const bf16*)x, reinterpret_cast<unsigned long long*>(st), HW, C, rpc);
-  if (int rc = check_launch("group_norm_bwd")) return rc;
+  long long* st_ws = reinterpret_cast<long long*>(ws);
+  double* gst = reinterpret_cast<double*>(st_ws + (size_t)B * C * 2);
+  const long long* st = x_stats ? x_stats : st_ws;
+  if (!x_stats) {
+    chan_stats_kernel<bf16><<<grid, threads, smem, s>>>((const bf16*)x, reinterpret_cast<unsigned long long*>(st_ws), HW, C, rpc);
+    if (int rc = check_launch("group_norm_bwd")) return rc;
+  }
   gn_bwd_pass_kernel<false><<<grid, threads, smem, s>>>((const bf16*)x, (const bf16*)dy, st, gst, gamma, beta, nullptr, nullptr, HW, C,
                                                         groups, eps, silu, rpc);
   if (int rc = check_launch("group_norm_bwd")) return rc;

@@ -603,7 +603,7 @@ static int attention_bwd_t(const AttnBwdParams& p, int B, cudaStream_t s) {
 
 // norm.cu: three coalesced passes (bf16, C % 8 == 0); returns -1 when the shape does not fit
 int group_norm_bwd_fast(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
-                        int B, int HW, int C, int groups, float eps, int silu, cudaStream_t s);
+                        const long long* x_stats, int B, int HW, int C, int groups, float eps, int silu, cudaStream_t s);
 
 // attn_bwd_tc.cu: tcgen05 kernels (bf16, head dims up to 192)
 struct AttnBwdArgs {
@@ -632,12 +632,12 @@ using namespace c2d;
 extern "C" {
 
 int c2d_group_norm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
-                       int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream) {
+                       const long long* x_stats, int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream) {
   C2D_REQUIRE(x && dy && gamma && beta && dx, "group_norm_bwd: null pointer");
   C2D_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "group_norm_bwd: bad dims");
   cudaStream_t s = (cudaStream_t)stream;
   if (ws && dtype == C2D_BF16 && C % 8 == 0 && C / 8 <= 512 && groups <= 32) {
-    const int rc = group_norm_bwd_fast(x, dy, gamma, beta, add, dx, ws, B, HW, C, groups, eps, silu, s);
+    const int rc = group_norm_bwd_fast(x, dy, gamma, beta, add, dx, ws, x_stats, B, HW, C, groups, eps, silu, s);
     if (rc >= 0) return rc;
   }
   dim3 grid(groups, B);

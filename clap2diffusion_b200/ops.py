@@ -805,7 +805,9 @@ def l2_normalize(x, eps: float = 1e-12, *, out=None):
 # ======================================================================================================
 # Backward / optimiser entry points of the stage-3 fine-tune step (include/c2d.h "stage-3 fine-tune step")
 # ======================================================================================================
-def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None):
+def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None, stats=None):
+    """Adjoint of GroupNorm(+SiLU).  stats: the int64 [B,C,2] channel statistics of x from the forward pass
+    (channel_stats / a GEMM epilogue); the bf16 path then skips its own statistics pass."""
     _dev(x)
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
@@ -814,10 +816,14 @@ def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=N
     if out is None:
         out = torch.empty_like(x)
     # scratch of the three-pass bf16 path: int64 channel statistics + double adjoint sums, zeroed per call
-    ws = torch.zeros(B * C * 4, device=x.device, dtype=torch.int64) if x.dtype == torch.bfloat16 and C % 8 == 0 else None
+    fast = x.dtype == torch.bfloat16 and C % 8 == 0
+    ws = torch.zeros(B * C * 4, device=x.device, dtype=torch.int64) if fast else None
+    if stats is not None:
+        assert stats.dtype == torch.int64 and stats.is_contiguous() and stats.numel() == B * C * 2
     with _Timed(0.0, 5 * _nb(x) + _nb(out)):
         check(lib.c2d_group_norm_bwd(x.data_ptr(), dy.data_ptr(), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), _ptr(add),
-                                     out.data_ptr(), _ptr(ws), B, HW, C, groups, float(eps), int(bool(silu)), _dt(x), _stream()),
+                                     out.data_ptr(), _ptr(ws), _ptr(stats) if fast else None, B, HW, C, groups, float(eps),
+                                     int(bool(silu)), _dt(x), _stream()),
               "group_norm_bwd")
     return out
 

@@ -97,12 +97,19 @@ class FrozenUNetGrad:
     # ---------------------------------------------------------------- layers (forward + recorded adjoint)
     def _gn(self, tp: _Tape, x, name, eps, silu):
         g, b = self.w[f"{name}.weight"], self.w[f"{name}.bias"]
-        y = ops.group_norm(x, g, b, GROUPS, eps, silu)
+        C = x.shape[-1]
+        stats = None
+        if x.dtype == torch.bfloat16 and C % 8 == 0 and C <= 4096:
+            # one statistics pass serves the forward (one-pass apply, the inference kernels) AND the adjoint
+            stats = ops.channel_stats(x, torch.zeros(x.shape[0] * C * 2, device=x.device, dtype=torch.int64))
+            y = ops.group_norm_apply(x, stats, g, b, GROUPS, eps, silu)
+        else:
+            y = ops.group_norm(x, g, b, GROUPS, eps, silu)
 
         def bwd():
             gy = tp.pop(y)
             if gy is not None and x.data_ptr() not in tp.stop:
-                tp.add_grad(x, ops.group_norm_bwd(x, gy.reshape(x.shape).contiguous(), g, b, GROUPS, eps, silu))
+                tp.add_grad(x, ops.group_norm_bwd(x, gy.reshape(x.shape).contiguous(), g, b, GROUPS, eps, silu, stats=stats))
         tp.ops.append(bwd)
         return y
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define C2D_ABI_VERSION 7   /* 7: c2d_adamw_step_sched, c2d_attention_lse, have_lse argument of c2d_attention_bwd; 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
+#define C2D_ABI_VERSION 7   /* 7: c2d_adamw_step_sched, c2d_attention_lse, have_lse argument of c2d_attention_bwd, x_stats argument of c2d_group_norm_bwd; 6: c2d_stft_frames_split, strided / typed c2d_power_spectrum, workspace argument of c2d_group_norm_bwd; 5: + backward / optimiser entry points of the stage-3 fine-tune step (c2d_*_bwd, c2d_adamw_step ...);
                              * 4: + c2d_destroy, c2d_set_workspace, c2d_splitk_workspace_bytes (the library owns no device
                              *    memory); 3: + c2d_xattn_* (fused cross-attention site), c2d_conv3x3_down */
 
@@ -259,9 +259,11 @@ int c2d_legacy_combine(const void* fg, const void* bg, const void* amb, const fl
  * output) is summed into the result: the fan-in of residual branches costs no extra pass. */
 /* GroupNorm(+SiLU) adjoint: statistics recomputed from x;  dx = d/dx [act(gn(x))] . dy (+ add).
  * ws (optional): caller-ZEROED scratch of B * C * 32 bytes -- with it the bf16 path runs as three coalesced passes
- * (channel statistics, adjoint sums, apply) instead of one CTA per (sample, group). */
+ * (channel statistics, adjoint sums, apply) instead of one CTA per (sample, group).  x_stats (optional, with ws): the
+ * [B][C][2] fixed-point channel statistics of x the forward pass already holds (c2d_channel_stats or a GEMM epilogue) --
+ * the statistics pass is skipped. */
 int c2d_group_norm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const void* add, void* dx, void* ws,
-                       int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
+                       const long long* x_stats, int B, int HW, int C, int groups, float eps, int silu, int dtype, void* stream);
 /* LayerNorm adjoint over the rows of x[M][C] (+ add) */
 int c2d_layer_norm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, int M, int C, float eps,
                        int dtype, void* stream);

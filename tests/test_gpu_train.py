@@ -45,6 +45,14 @@ def test_group_norm_bwd(B, HW, C, silu, dtype):
         got = ops.group_norm_bwd(x, dy, g, b, 32, 1e-5, silu, add=a)
         ref = T.group_norm_bwd(x.cpu(), dy.cpu(), g.cpu(), b.cpu(), 32, 1e-5, silu, add=None if a is None else a.cpu())
         assert rel(got, ref) < tol(dtype)
+    if dtype == BF16:       # the forward pass's channel statistics handed to the adjoint: same result, no statistics pass
+        st = ops.channel_stats(x, torch.zeros(B * C * 2, device=DEV, dtype=torch.int64))
+        n0 = ops._lib.launch_count()
+        got2 = ops.group_norm_bwd(x, dy, g, b, 32, 1e-5, silu, add=add, stats=st)
+        n1 = ops._lib.launch_count()
+        ops.group_norm_bwd(x, dy, g, b, 32, 1e-5, silu, add=add)
+        print("launches with / without forward statistics:", n1 - n0, ops._lib.launch_count() - n1)
+        assert rel(got2, got) < 1e-3 and n1 - n0 < ops._lib.launch_count() - n1
 
 
 @pytest.mark.parametrize("dtype", [F32, BF16])

@@ -422,7 +422,7 @@ def _vjp(fn, inputs, gy):
         return torch.autograd.grad(y, xs, gy.float().reshape(y.shape))
 
 
-def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None):
+def group_norm_bwd(x, dy, gamma, beta, groups=32, eps=1e-5, silu=False, *, add=None, out=None, stats=None):
     B, C = x.shape[0], x.shape[-1]
 
     def f(t):
