@@ -3,6 +3,8 @@ of the same op, and the whole step -- frozen-UNet reverse pass through libc2d ke
 oracle (oracle/sd15.py on the GPU as the checker).  Gates: fp32 mode <= 1e-3 relative L2 per gradient tensor, bf16
 mode cosine >= 0.99 and relative L2 <= 1e-1 per tensor, 1.5e-1 for the three gate scalars (bf16 activations AND bf16
 activation gradients through ~600 layers)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -17,6 +19,7 @@ from clap2diffusion_b200.models.hierarchical_audio_v4 import ImprovedHierarchica
 from clap2diffusion_b200.train import LEVELS, Stage3Trainer
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEV = "cuda"
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -263,3 +266,31 @@ def test_stage3_step_as_cuda_graph_matches_eager(W):
     assert float((gr.flat - eager.flat).norm()) < 1e-3 * moved          # double atomics in the GroupNorm adjoint: order-dependent rounding only
     with pytest.raises(ValueError):
         gr.train_step(make_batch(B=2, h=8, w=8))
+
+
+def test_train_stage3_cli_writes_reference_layout(tmp_path):
+    """scripts/train_stage3.py (the reference's configuration keys and file names): a few graph-replayed steps on batches
+    in the reference's format, then unet_adapter_final.pth in the layout scripts/inference.py loads."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("train_stage3_cli", os.path.join(ROOT, "scripts", "train_stage3.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    data = tmp_path / "data"
+    data.mkdir()
+    for i in range(2):
+        b = make_batch(B=2, h=16, w=16, seed=40 + i)
+        torch.save({k: b[k] for k in ("audio_embedding", "image_latents", "text_embedding")}, data / f"batch{i}.pt")
+    ck = tmp_path / "ck"
+    tr = cli.main(["--checkpoint-dir", str(ck), "--data", str(data), "--num-steps", "4", "--batch-size", "2", "--learning-rate", "1e-3",
+                   "--log-interval", "2", "--save-interval", "4"])
+    assert tr.step_count == 4 and tr._graph is not None
+    saved = torch.load(ck / "unet_adapter_final.pth", weights_only=True)
+    assert saved["mode"] == "add" and saved["step"] == 4
+    for lvl in LEVELS:
+        for k, v in tr.procs[lvl].state_dict().items():
+            assert torch.equal(saved[f"processor_{lvl}"][k], v.detach().cpu())
+    full = torch.load(ck / "audio_projector_stage3_finetuned.pth", weights_only=True)
+    assert {"step", "hierarchical_state_dict", "optimizer_state_dict", "config"} <= set(full) and full["config"]["gradient_clipping"] == 0.5
+    # resume: the processors just written are picked up
+    unet_sd, hier, procs = cli.load_models(ck, torch.device(DEV), 0)
+    assert procs is not None and torch.equal(procs["mid"]["alpha"], saved["processor_mid"]["alpha"])

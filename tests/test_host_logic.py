@@ -2,6 +2,8 @@
 module plumbing, sampler, schedulers) checked on CPU against the oracle and the reference-generated golden
 vectors, with the libc2d-backed ops swapped for the torch test double (tests/torch_ops.py).  The CUDA
 kernels themselves are checked by the -m gpu tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -17,6 +19,9 @@ from clap2diffusion_b200 import schedulers
 from clap2diffusion_b200.models import audio_adapter_v4 as padapter
 from clap2diffusion_b200.models import audio_attention_processor as pproc
 from clap2diffusion_b200.models import hierarchical_audio_v4 as phier
+
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _t(a):
@@ -465,3 +470,21 @@ def test_evaluate_and_gradio_surface_without_gpu():
         assert callable(mod.main)
     sig = inspect.signature(mod.AudioToImageGenerator.generate)
     assert list(sig.parameters)[1:] == ["audio_path", "text_prompt", "norm_value", "num_steps", "cfg_scale", "seed", "model_type"]
+
+
+def test_train_stage3_cli_surface():
+    """scripts/train_stage3.py keeps the reference's configuration keys and defaults (main :275-286, gradient accumulation
+    aside: the global batch comes from the GPUs) and refuses to run without a CUDA device."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("train_stage3_cli", os.path.join(ROOT, "scripts", "train_stage3.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    assert cli.DEFAULTS == {"learning_rate": 1e-5, "weight_decay": 0.01, "num_steps": 1000, "batch_size": 2,
+                            "gradient_clipping": 0.5, "checkpoint_dir": "../checkpoints", "save_interval": 500, "log_interval": 50}
+    b = cli.Batches(None, 3, 8, rank=1, seed=0)(5)
+    assert tuple(b["audio_embedding"].shape) == (3, 512) and tuple(b["image_latents"].shape) == (3, 4, 8, 8)
+    assert tuple(b["text_embedding"].shape) == (3, 77, 768) and tuple(b["noise"].shape) == (3, 4, 8, 8)
+    assert b["timesteps"].dtype == torch.int64 and int(b["timesteps"].max()) < 1000
+    if not torch.cuda.is_available():
+        with pytest.raises(SystemExit):
+            cli.main(["--num-steps", "1"])
