@@ -13,6 +13,9 @@
 //              P (bf16, off-diagonal blocks = 0) written IN PLACE over S in TMEM (64 packed columns)
 //              O [128 x 32] = P V                8 TS MMAs (A = P from TMEM, B = V MN-major from its natural rows)
 //              O / sum -> bf16 -> global
+//   (Measured and rejected: several window pairs per CTA with the head loop outside, so that the bias is staged once per
+//   head -- 433 -> 647 us at the 64 x 64 stage: the four heads of a token share cache lines, and walking other windows
+//   between them loses that L1 reuse.)
 //   TMEM: 128 columns per CTA (S | P in place | O over the dead upper half of S) -> three CTAs per SM (67 KB of shared
 //   memory each) hide each other's serial chain (gather -> MMA -> softmax -> MMA -> store).
 #include <stdlib.h>
