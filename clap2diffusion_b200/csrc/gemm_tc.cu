@@ -556,10 +556,10 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
 // i+1, and the TMA producer runs ahead across tile boundaries through a deeper smem ring.  Removes the
 // per-tile prologue (TMEM alloc, barrier init, pipeline fill) that dominated the short-K projections.
 // =====================================================================================================
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct Tc2Cfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * TC_BK * 2;      // CTA pair: each CTA stages half of the B rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns between accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -571,11 +571,26 @@ struct Tc2Cfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
-template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
-  using Cfg = Tc2Cfg<BN, STAGES>;
+// PAIR: the same persistent schedule on a CTA pair (cta_group::2, cluster of two CTAs on the SMs of a TPC): a tile is 256 rows
+// x BN columns, each CTA stages its own 128 A rows and HALF of the B rows and keeps its 128 x BN accumulators (double-buffered)
+// in its own TMEM; the leader issues the MMAs for both.  Per SM and k-block (128 + BN / 2) x 64 operand elements come
+// through L2 -> shared memory instead of (128 + BN) x 64: the K = 320 GEGLU projection is bound by exactly that traffic.
+// Protocol on top of the single-CTA one: TMA bytes of both CTAs are counted on the LEADER's full[s]; the leader's commits
+// are multicast to both CTAs' empty[s] / tfull[b]; both CTAs' epilogue threads arrive on the LEADER's tempty[b].
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF, bool PAIR>
+__device__ __forceinline__ void gemm_tc2_body(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                                              const TcParams& p, const int num_tiles, const int num_n) {
+  using Cfg = Tc2Cfg<BN, STAGES, PAIR>;
+  static_assert(!PAIR || !CONV, "the persistent pair kernel serves the linears (the convolutions use gemm_tc3_kernel)");
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // tile walk: a work item is a 128-row (PAIR: 256-row) x BN-column tile; `first` / `step` in work items
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int t) { return PAIR ? ((t / num_n) * 2 + (int)rank) * TC_BM : (t / num_n) * TC_BM; };
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -591,12 +606,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32 * TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR ? 2 : 1) * 32 * TC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // barrier inits and the TMEM allocation are visible to the peer CTA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();           // everything above overlapped the predecessor's tail; global memory is touched from here on
@@ -605,8 +624,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer (runs ahead across tiles; converged warp, elected lane issues) =====================
     uint32_t kbc = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
+    for (int t = first; t < num_tiles; t += step) {
+      const int m0 = tile_m0(t), n0 = (t % num_n) * BN;
       int b0 = 0, y0 = 0, x0 = 0;
       if (CONV) {
         b0 = m0 / p.HW;
@@ -620,17 +639,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
           uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-          if (CONV) {
-            const int tap = kb / p.cblocks;
-            const int c0 = (kb - tap * p.cblocks) * TC_BK;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - p.cpad, y0 * p.cstride + ky - p.cpad, b0);
-            tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
+          if constexpr (PAIR) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);      // both CTAs' bytes land on the leader
+            const uint32_t lbar = mapa_rank0(smem_u32(&full[s]));
+            if (kb < p.kb_split) tma_load_2d_2sm(sA, &tmA, lbar, kb * TC_BK, m0);
+            else tma_load_2d_2sm(sA, &tmA2, lbar, (kb - p.kb_split) * TC_BK, m0);
+            tma_load_2d_2sm(sB, &tmB, lbar, kb * TC_BK, n0 + (int)rank * (BN / 2));
           } else {
-            if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
-            else tma_load_2d(sA, &tmA2, &full[s], (kb - p.kb_split) * TC_BK, m0);
-            tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
+            mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            if (CONV) {
+              const int tap = kb / p.cblocks;
+              const int c0 = (kb - tap * p.cblocks) * TC_BK;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(sA, &tmA, &full[s], c0, x0 * p.cstride + kx - p.cpad, y0 * p.cstride + ky - p.cpad, b0);
+              tma_load_2d(sB, &tmB, &full[s], tap * p.Cin + c0, n0);
+            } else {
+              if (kb < p.kb_split) tma_load_2d(sA, &tmA, &full[s], kb * TC_BK, m0);
+              else tma_load_2d(sA, &tmA2, &full[s], (kb - p.kb_split) * TC_BK, m0);
+              tma_load_2d(sB, &tmB, &full[s], kb * TC_BK, n0);
+            }
           }
         }
         __syncwarp();
@@ -638,12 +665,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN, 0, 0);
     const uint64_t desc0 = make_desc_k_sw128(smem_u32(smem));
     uint32_t kbc = 0, it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    if (!PAIR || rank == 0)                                      // CTA pair: the leader issues for both
+    for (int t = first; t < num_tiles; t += step, ++it) {
       const uint32_t buf = it & 1u;
-      mbar_wait(&tempty[buf], ((it >> 1) & 1u) ^ 1u);          // epilogue drained this accumulator
+      mbar_wait(&tempty[buf], ((it >> 1) & 1u) ^ 1u);          // epilogue (of both CTAs) drained this accumulator
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < p.num_k_blocks; ++kb, ++kbc) {
@@ -653,11 +681,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
           const uint64_t a_desc = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
           const uint64_t b_desc = a_desc + (uint64_t)(Cfg::A_BYTES >> 4);
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_f16(acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
-          if (kb == p.num_k_blocks - 1) umma_commit(&tfull[buf]);
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16_2sm(acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[s]);                               // frees the slot in both CTAs
+            if (kb == p.num_k_blocks - 1) umma_commit_2sm(&tfull[buf]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_f16(acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);
+            if (kb == p.num_k_blocks - 1) umma_commit(&tfull[buf]);
+          }
         }
         __syncwarp();
       }
@@ -671,10 +707,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool vec_r = p.residual && (p.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     uint32_t it = 0;
     longlong2 ln_raw = make_longlong2(0, 0);
-    if (LNF) ln_raw = ln_row_load(p, (blockIdx.x / num_n) * TC_BM + q * 32 + lane);    // first tile's row statistics
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    if (LNF && first < num_tiles) ln_raw = ln_row_load(p, tile_m0(first) + q * 32 + lane);    // first tile's row statistics
+    const uint32_t tempty_leader[2] = {PAIR ? mapa_rank0(smem_u32(&tempty[0])) : 0u, PAIR ? mapa_rank0(smem_u32(&tempty[1])) : 0u};
+    auto acc_drained = [&](uint32_t buf) {       // this thread has read its last accumulator column of the tile
+      tc_fence_before();
+      if constexpr (PAIR) mbar_arrive_cluster(tempty_leader[buf]);
+      else mbar_arrive(&tempty[buf]);
+    };
+    for (int t = first; t < num_tiles; t += step, ++it) {
       const uint32_t buf = it & 1u;
-      const int m0 = (t / num_n) * TC_BM, n0 = (t % num_n) * BN;
+      const int m0 = tile_m0(t), n0 = (t % num_n) * BN;
       const int nbase = GEGLU ? (n0 >> 1) : n0;
       // this tile's bias slice (+ the row vector when the whole tile shares one) -> smem
       const bool rv_shared = p.rowvec && (m0 / p.rows_per_vec) == ((min(m0 + TC_BM, p.M) - 1) / p.rows_per_vec);
@@ -699,8 +741,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (LNF) {
         ln_row_finish(p, ln_raw, ln_rstd, ln_mr);
         // the next tile's statistics travel while this tile drains
-        const int tn = t + gridDim.x;
-        if (tn < num_tiles) ln_raw = ln_row_load(p, (tn / num_n) * TC_BM + q * 32 + lane);
+        const int tn = t + step;
+        if (tn < num_tiles) ln_raw = ln_row_load(p, tile_m0(tn) + q * 32 + lane);
       }
       mbar_wait(&tfull[buf], (it >> 1) & 1u);
       tc_fence_after();
@@ -715,7 +757,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32(t_row + c * 32, r);
           tmem_ld_wait();
-          if (c == c_last) { tc_fence_before(); mbar_arrive(&tempty[buf]); }     // this warp is done with the accumulator
+          if (c == c_last) acc_drained(buf);                                     // this warp is done with the accumulator
           epi_affine32<LNF>(r, sb + c * 32, scs + c * 32, ln_rstd, -ln_mr, v);
           if (p.rowvec && !rv_shared) {
             const int m = m0 + q * 32 + lane;
@@ -733,7 +775,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld_32x32(t_row + ca, ra);
           tmem_ld_32x32(t_row + ca + 64, rg);
           tmem_ld_wait();
-          if (c == c_last) { tc_fence_before(); mbar_arrive(&tempty[buf]); }
+          if (c == c_last) acc_drained(buf);
           float gg[32];
           epi_affine32<LNF>(ra, sb + ca, scs + ca, ln_rstd, -ln_mr, v);
           epi_affine32<LNF>(rg, sb + ca + 64, scs + ca + 64, ln_rstd, -ln_mr, gg);
@@ -805,11 +847,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer may still read this CTA's smem / TMEM until its last MMA has retired
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+}
+
+template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
+  gemm_tc2_body<BN, STAGES, CONV, GEGLU, LNF, false>(tmA, tmA2, tmB, p, num_tiles, num_n);
+}
+
+// persistent CTA pair (see gemm_tc2_body): num_tiles counts 256-row x BN tiles
+template <int BN, int STAGES, bool GEGLU, bool LNF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const TcParams p, const int num_tiles, const int num_n) {
+  gemm_tc2_body<BN, STAGES, false, GEGLU, LNF, true>(tmA, tmA2, tmB, p, num_tiles, num_n);
 }
 
 template <int BN, int STAGES, bool CONV, bool GEGLU, bool LNF = false>
@@ -823,6 +882,20 @@ static int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   launch_pdl(gemm_tc2_kernel<BN, STAGES, CONV, GEGLU, LNF>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p, num_tiles, num_n);
   return check_launch(CONV ? "conv3x3_tc" : (GEGLU ? "geglu_linear_tc" : "linear_tc"));
+}
+
+template <int BN, int STAGES, bool GEGLU, bool LNF = false>
+static int launch_tc4(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+  using Cfg = Tc2Cfg<BN, STAGES, true>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "persistent pair GEMM smem");
+  static int smem_set[C2D_MAX_DEVICES] = {};
+  if (int rc = ensure_dyn_smem(gemm_tc4_kernel<BN, STAGES, GEGLU, LNF>, Cfg::SMEM_BYTES, smem_set, "gemm_tc4")) return rc;
+  const int num_n = ceil_div(p.N, BN);
+  const int num_tiles = num_n * ceil_div(ceil_div(p.M, TC_BM), 2);
+  const int pairs = num_sms() / 2;
+  const int clusters = num_tiles < pairs ? num_tiles : pairs;
+  launch_pdl(gemm_tc4_kernel<BN, STAGES, GEGLU, LNF>, dim3(2 * clusters), dim3(TC_THREADS), Cfg::SMEM_BYTES, s, tmA, tmA2, tmB, p, num_tiles, num_n);
+  return check_launch(GEGLU ? "geglu_linear_tc" : "linear_tc");
 }
 
 // =====================================================================================================
@@ -1240,6 +1313,19 @@ static bool geglu_pair_enabled() {
   }
   return v == 1;
 }
+// C2D_PPAIR=geglu | all: the persistent CTA-pair kernel (gemm_tc4_kernel) for the GEGLU projection / for every persistent linear.
+// Measured at UNet batch 16 (tools/bench_shapes.py, graph-timed) against the single-CTA persistent kernel: it wins where the
+// main loop is long -- GEGLU K = 1280: 81.4 -> 71.7 us (1498 TFLOP/s), linears 16384 x 640 x 1280: 28.9 -> 25.1, x 2560:
+// 53.8 -> 50.2 us -- is level at K = 640 and LOSES at K = 320 (GEGLU 124 -> 139 us, QKV 66 -> 77 us): every 1.4 us tile
+// pays the cross-CTA tfull / tempty round trips.  Worth ~0.07 ms of a 17.5 ms step in total, so it stays opt-in.
+static int ppair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("C2D_PPAIR");
+    v = !e ? 0 : (e[0] == 'g' ? 1 : (e[0] == 'a' ? 2 : 0));
+  }
+  return v;
+}
 // auto: persistent for the GEGLU projection and for the large-M linears whose main loop is long enough (K >= 640)
 // or whose output is wide enough (N >= 960) for the cross-tile prefetch to pay (measured: -5 .. -16 %)
 static bool use_persistent(bool geglu = false, int M = 0, int N = 0, int K = 0) {
@@ -1315,9 +1401,11 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   const bool ln_or_rs = lnx;       // these epilogues exist in the BN = 160 / 128 single-CTA kernels only
   const bool persist = use_persistent(geglu, M, N, K) && !(ex && ex->rowstats_out);
   (void)ln_or_rs;
+  const bool ppair = !pairk && persist && M >= 512 && ((geglu && ppair_mode() >= 1 && N % 256 == 0) || (!geglu && ppair_mode() == 2));
   int BN = pairk ? (geglu ? (N % 256 == 0 ? 256 : 128) : pick_bn_pair(N))
                  : (geglu ? (persist ? pick_bn_geglu(M, N) : 128) : ((persist && !(ex && ex->ln_stats)) ? pick_bn(M, N) : wide_bn(N)));
   // small M (the low-resolution levels, single-image latency): the wide tile leaves most SMs idle -> 64-column tiles
+  if (ppair && !geglu) BN = (N % 160 == 0) ? 160 : 128;
   if (!pairk && !geglu && !persist && small_bn_enabled() && N % 64 == 0 &&
       ceil_div(M, TC_BM) * ceil_div(N, BN) * 2 <= num_sms())
     BN = 64;
@@ -1341,7 +1429,7 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t st[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {TC_BK, (uint32_t)(pairk ? BN / 2 : BN)};
+    uint32_t box[2] = {TC_BK, (uint32_t)((pairk || ppair) ? BN / 2 : BN)};
     int rc = make_tmap_bf16(&tmB, w, 2, dims, st, box);
     if (rc) return rc;
   }
@@ -1366,6 +1454,11 @@ int linear_tc(const void* x, const void* w, const float* bias, const float* rowv
     return launch_tc3<128, 4, false, false>(tmA, tmA2, tmB, p, s);
   }
   const bool lnf = p.ln_stats != nullptr;
+  if (ppair) {
+    if (geglu) return lnf ? launch_tc4<256, 5, true, true>(tmA, tmA2, tmB, p, s) : launch_tc4<256, 5, true, false>(tmA, tmA2, tmB, p, s);
+    if (BN == 160) return lnf ? launch_tc4<160, 6, false, true>(tmA, tmA2, tmB, p, s) : launch_tc4<160, 6, false, false>(tmA, tmA2, tmB, p, s);
+    return lnf ? launch_tc4<128, 6, false, true>(tmA, tmA2, tmB, p, s) : launch_tc4<128, 6, false, false>(tmA, tmA2, tmB, p, s);
+  }
   if (geglu && lnf) {                                                                         // folded-LN GEGLU: persistent only
     if (BN == 256) return launch_tc2<256, 3, false, true, true>(tmA, tmA2, tmB, p, s);
     return launch_tc2<128, 5, false, true, true>(tmA, tmA2, tmB, p, s);
