@@ -1360,8 +1360,9 @@ static int pick_bn(int M, int N) {
 }
 
 // GEGLU projection on the persistent kernel: 128 x 256 tiles.  One N = 256 MMA per k-step costs 162 issue cycles against
-// 2 x 98 for two N = 128 ones, and the A tile is re-streamed from L2 half as often (the K = 320 sites are L2 -> SM bound:
-// knocking out 3 of 4 MMAs did not change their time).  Measured at UNet batch 16 (tools/bench_shapes.py), BN 128 -> 256:
+// 2 x 98 for two N = 128 ones, and a tile pays its fixed epilogue / hand-over latencies once per 256 columns (the K = 320
+// sites are NOT tensor bound: knocking out 3 of 4 MMAs did not change their time; an A-stationary walk that cut their
+// operand traffic by a third did not either -- DESIGN.md section 7).  Measured at UNet batch 16 (tools/bench_shapes.py), BN 128 -> 256:
 // 143 -> 128, 113 -> 91, 103 -> 82, 31 -> 26 us for the four levels.  C2D_GEGLU_BN=128 forces the narrow tile (A/B runs).
 static int pick_bn_geglu(int M, int N) {
   (void)M;
