@@ -24,6 +24,8 @@ class Sampler:
         self.unet, self.hier, self.vae = unet, hier, vae
         self.use_graph = use_graph
         self._graphs: Dict[tuple, dict] = {}
+        self._plans: Dict[tuple, tuple] = {}          # (scheduler, steps) -> (plan, time-embedding table, coefficients)
+        self._vae_graphs: Dict[tuple, dict] = {}      # latent shape -> captured VAE decode
         self.replayed_launches = 0      # kernels launched through graph replays (not seen by c2d_launch_count)
 
     # ------------------------------------------------------------------ conditioning (once per batch)
@@ -64,11 +66,15 @@ class Sampler:
         Returns dict(latents [B,4,H,W] fp32, image [B,3,8H,8W] fp32 if decode, trace [list] if trace)."""
         unet = self.unet
         B, _, H, W = noise.shape
-        plan = make_plan(scheduler, steps)
+        # the schedule's constants (scheduler coefficients, the frozen time-embedding rows of its timesteps) depend on
+        # (scheduler, steps) only: built once, not once per image
+        pk = (scheduler, int(steps))
+        if pk not in self._plans:
+            plan = make_plan(scheduler, steps)
+            self._plans[pk] = (plan, unet.time_table(plan.timesteps), torch.from_numpy(plan.coef).to(unet.device))
+        plan, table, coefs = self._plans[pk]
         n_run = steps if max_steps is None else min(steps, max_steps)
         kv = self.condition(clap, ctx_cond, ctx_uncond, use_audio)
-        table = unet.time_table(plan.timesteps)
-        coefs = torch.from_numpy(plan.coef).to(unet.device)
         # static state (and the captured graph) is cached per problem shape; fresh K/V are copied into the
         # buffers the graph was captured on
         key = (B, H, W, float(guidance), tuple(sorted((n, tuple(t.shape)) for n, t in kv.items() if t is not None)))
@@ -103,8 +109,32 @@ class Sampler:
         if trace:
             out["trace"] = traces
         if decode and self.vae is not None:
-            out["image"] = self.vae.decode(out["latents"])
+            out["image"] = self._decode(out["latents"])
         return out
+
+    def _decode(self, latents: torch.Tensor) -> torch.Tensor:
+        """VAE decode; replayed from a CUDA graph per latent shape (~150 eager launches cost ~3 ms of host time per image
+        batch, which is all exposed in the single-image latency)."""
+        if not self.use_graph:
+            return self.vae.decode(latents)
+        key = tuple(latents.shape)
+        st = self._vae_graphs.get(key)
+        if st is None:
+            z = latents.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.vae.decode(z)                       # lazy attribute / workspace setup must not happen during capture
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                img = self.vae.decode(z)
+            st = self._vae_graphs[key] = {"z": z, "graph": g, "img": img, "launches": _lib.launch_count() - n0}
+        st["z"].copy_(latents)
+        st["graph"].replay()
+        self.replayed_launches += st["launches"]
+        return st["img"].clone()
 
     def _capture(self, st: dict):
         """Warm up once on a side stream (lazy attribute / workspace setup must not happen during capture),
