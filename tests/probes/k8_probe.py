@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Audio-side modules (projector / decomposer MLPs) in bf16 on the tcgen05 GEMM: error against the reference goldens and
-the kernels each op resolves to (GPU only)."""
+the kernels each op resolves to (GPU only).  Lives under tests/ because it checks against the oracle (test infrastructure)."""
 import os
 import sys
 from collections import Counter
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402

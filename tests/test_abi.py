@@ -53,3 +53,18 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package, scripts/, app/ or tools/ imports it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for sub in ("clap2diffusion_b200", "scripts", "app", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders

@@ -6,25 +6,27 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle import pipeline as PL  # noqa: E402
-from test_train_host_logic import make_batch  # noqa: E402
-from clap2diffusion_b200 import ops  # noqa: E402
+from clap2diffusion_b200 import ops, synthetic  # noqa: E402
+from clap2diffusion_b200 import unet as unet_mod  # noqa: E402
 from clap2diffusion_b200.models.hierarchical_audio_v4 import ImprovedHierarchicalAudioEncoder  # noqa: E402
-from clap2diffusion_b200.train import LEVELS, Stage3Trainer  # noqa: E402
+from clap2diffusion_b200.train import Stage3Trainer  # noqa: E402
 
 dt = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else torch.float32
 hw = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-W = PL.build_weights(seed=0, with_vae=False)
+torch.manual_seed(0)
+usd = synthetic.random_state_dict(unet_mod.param_shapes(), 0, "cuda")
 hier = ImprovedHierarchicalAudioEncoder().to("cuda").eval()
-hier.load_state_dict({k: v.to("cuda") for k, v in W["hier"].items()})
-tr = Stage3Trainer(W["unet"], hier, {l: W[f"proc_{l}"] for l in LEVELS}, device="cuda", dtype=dt)
-batch = make_batch(B=min(B, 4), h=hw, w=hw)
-if B > 4:
-    batch = {k: v.repeat(*( [B // 4] + [1] * (v.dim() - 1))) for k, v in make_batch(B=4, h=hw, w=hw).items()}
+tr = Stage3Trainer(usd, hier, None, device="cuda", dtype=dt)
+g = torch.Generator().manual_seed(1234)
+batch = {"audio_embedding": torch.from_numpy(np.stack([synthetic.clap_embedding(k) for k in range(B)])),
+         "image_latents": torch.randn(B, 4, hw, hw, generator=g),
+         "text_embedding": torch.from_numpy(np.stack([synthetic.text_states(f"prompt {k % 8}") for k in range(B)])),
+         "noise": torch.randn(B, 4, hw, hw, generator=g), "timesteps": torch.randint(0, 1000, (B,), generator=g)}
+batch = {k: v.to("cuda") for k, v in batch.items()}
 torch.cuda.synchronize()
 for i in range(3):
     t0 = time.time()
