@@ -151,7 +151,8 @@ int c2d_attention(const void* q, const void* k, const void* v, void* o, int B, i
                   long long ldq, long long ldk, long long ldv, long long ldo, long long bsq, long long bsk,
                   long long bsv, long long bso, float scale, const uint8_t* mask, int dtype, int impl,
                   void* stream);
-/* Training forward: the same call with an optional by-product for c2d_attention_bwd -- lse [B][heads][Nq] fp32, the per-row
+/* Training forward (the attention of models/audio_attention_processor.py:124-131 / diffusers' SDPA under autograd in the reference's
+ * scripts/train_stage3.py:177-180): the same call with an optional by-product for c2d_attention_bwd -- lse [B][heads][Nq] fp32, the per-row
  * log-sum-exp of the scaled scores in the log2 domain (max + log2(sum 2^(s - max)), s = scale * log2(e) * q.k).  Only the
  * long-sequence tcgen05 kernel (head_dim <= 64, Nkv > 128) produces it; *lse_written (host) says whether this call did. */
 int c2d_attention_lse(const void* q, const void* k, const void* v, void* o, int B, int heads, int Nq, int Nkv, int d,
@@ -302,7 +303,8 @@ int c2d_sumsq(const float* x, long long n, double* out, void* stream);
 int c2d_clip_scale(const double* sumsq, float max_norm, float* scale, float* norm_out, void* stream);
 int c2d_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
-/* The same update with the schedule in device memory -- sched [sched_len][3] = (learning rate, 1 - beta1^(t+1), 1 - beta2^(t+1))
+/* (replaces optimizer.step() + scheduler.step() of scripts/train_stage3.py:188-189 with the AdamW / CosineAnnealingLR set up at :33-46)
+ * The same update with the schedule in device memory -- sched [sched_len][3] = (learning rate, 1 - beta1^(t+1), 1 - beta2^(t+1))
  * of optimiser step t, *step_dev = steps taken so far (the caller increments it) -- so that the launch can live in a CUDA graph
  * replayed once per training step. */
 int c2d_adamw_step_sched(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* sched,
